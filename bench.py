@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine E]
+
+Workload (BASELINE.json configs[1]): RDN-CiaoSR (config 001: RDN 16 blocks x 8 layers,
+growth 64; imnet_{q,k,v} hidden 256x4; cross-scale attention on), a batch of 16 LR
+48x48 crops -> x4 (192x192), i.e. 589 824 HR pixels per step per GPU, eval_bsize 30000,
+synthetic weights and inputs (the reference ships no checkpoints or data).
+
+A step = one `generator(lq, coord, cell, test_mode=True)` call: the PyTorch RDN encoder
+followed by the native head.  `value` times it with inputs resident in HBM; `e2e` times the
+restorer call a user makes (`model(lq, test_mode=True, coord=, cell=)`, ciaosr.py:111-203)
+from pinned host buffers, result back on the host.  N > 1: weak scaling, every rank runs its
+own batch and the ranks all-gather the final RGB (the only collective on the path).
+
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port of it;
+the reference itself needs mmcv/mmedit and cannot be installed) on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "Mpix/s (HR out) RDN-CiaoSR x4 48->192"
+B, H, W, SCALE, C = 16, 48, 48, 4, 64
+HIDDEN = [256, 256, 256, 256]
+EVAL_BSIZE = 30000
+RGB_MEAN = (0.4488, 0.4371, 0.4040)
+
+
+def model_cfg(engine="auto"):
+    from ciaosr_b200.generators import LocalImplicitSRRDN
+    from ciaosr_b200.restorers import CiaoSR
+    mlp = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3, hidden_list=list(HIDDEN))
+    return dict(type=CiaoSR,
+                generator=dict(type=LocalImplicitSRRDN,
+                               encoder=dict(type="RDN", in_channels=3, out_channels=3, mid_channels=C,
+                                            num_blocks=16, upscale_factor=4, num_layers=8,
+                                            channel_growth=64),
+                               imnet_q=mlp(), imnet_k=mlp(), imnet_v=mlp(), feat_unfold=True,
+                               eval_bsize=EVAL_BSIZE, engine=engine),
+                rgb_mean=RGB_MEAN, rgb_std=(1., 1., 1.),
+                pixel_loss=dict(type="L1Loss", loss_weight=1.0, reduction="mean"))
+
+
+def build_model(engine="auto"):
+    from ciaosr_b200 import synth
+    from ciaosr_b200.builder import build
+    m = build(model_cfg(engine), test_cfg=dict(scale=SCALE))
+    synth.fill_module(m.generator, 0)
+    return m.eval()
+
+
+def make_inputs(batch, seed):
+    from ciaosr_b200 import synth
+    from ciaosr_b200.coords import make_cell, make_coord
+    lq = synth.synth_lr_image(batch, H, W, seed) + torch.tensor(RGB_MEAN).view(1, 3, 1, 1)  # raw [0,1)
+    th, tw = H * SCALE, W * SCALE
+    coord = make_coord((th, tw)).unsqueeze(0).expand(batch, -1, 2).contiguous()
+    cell = make_cell((th, tw), th * tw).unsqueeze(0).expand(batch, -1, 2).contiguous()
+    return lq, coord, cell
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        busy = sorted(v for v in sm if v >= 0.5 * max(sm)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def cpu_reference_sample(steps, warmup, threads):
+    """The reference's algorithm on host cores: RDN encoder (torch CPU) + oracle head with
+    the reference's eval_bsize chunking (cross-scale attention recomputed per chunk)."""
+    from oracle import ciaosr_oracle as orc
+    torch.set_num_threads(threads)
+    m = build_model()
+    g = m.generator
+    w = {k: v.detach() for k, v in g.state_dict().items()}
+    lq, coord, cell = make_inputs(1, 1)
+    lq = lq - torch.tensor(RGB_MEAN).view(1, 3, 1, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            feat = g.gen_feature(lq)[0]
+            out = orc.head_forward(lq, feat, coord, cell, w, eval_bsize=EVAL_BSIZE)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert out.shape == (1, H * SCALE * W * SCALE, 3)
+    px = H * SCALE * W * SCALE
+    mean = sum(times) / len(times)
+    return px / mean / 1e6, mean * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    val, ms = cpu_reference_sample(steps, warmup, threads)
+    sample = f"1 of the {B} LR 48x48 crops -> x4 (36 864 px) per step, {steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RDN-CiaoSR config 001, 48x48 -> x4, CPU sample of the batch-16 workload",
+                   "eval_bsize": EVAL_BSIZE, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    args.warmup = max(args.warmup, 3)
+    import torch.distributed as dist
+    from ciaosr_b200 import native
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the head)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = build_model(args.engine).to(dev)
+    gen = model.generator
+    lq_h, coord_h, cell_h = make_inputs(B, 100 + rank)
+    lq_h, coord_h, cell_h = lq_h.pin_memory(), coord_h.pin_memory(), cell_h.pin_memory()
+    lq_d = ((lq_h - torch.tensor(RGB_MEAN).view(1, 3, 1, 1))).to(dev)     # normalised, as forward_test passes it
+    coord_d, cell_d = coord_h.to(dev), cell_h.to(dev)
+    npx = B * H * SCALE * W * SCALE
+    gather = [torch.empty(B, H * SCALE * W * SCALE, 3, device=dev) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        with torch.no_grad():
+            out = gen(lq_d, coord_d, cell_d, test_mode=True)
+        if world > 1:
+            dist.all_gather(gather, out)
+        return out
+
+    out_h = torch.empty(B, H * SCALE * W * SCALE, 3).pin_memory()
+    in_bytes = lq_h.numel() * 4 + coord_h.numel() * 4 + cell_h.numel() * 4
+    out_bytes = out_h.numel() * 4
+
+    def step_e2e():
+        res = model(lq=lq_h.to(dev, non_blocking=True), gt=None, test_mode=True,
+                    coord=coord_h.to(dev, non_blocking=True), cell=cell_h.to(dev, non_blocking=True))
+        return res["output"]                       # forward_test moves it to the host (ciaosr.py:181)
+
+    def timed(fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        if profile:
+            native.profile_read()
+            native.profile_enable(True)
+        l0 = native.launch_count()
+        for s, e in ev:
+            flush.zero_()                          # L2 flush between timed iterations (not timed)
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        launches = native.launch_count() - l0
+        stages = None
+        if profile:
+            native.profile_enable(False)
+            stages = native.profile_read()
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, launches, stages
+
+    for _ in range(args.warmup):
+        step_device()
+    with ClockSampler(local) as clk:
+        ms_step, launches, stages = timed(step_device, args.steps, profile=True)
+    clocks = clk.summary()
+    # head alone (feature resident): what the roofline explains
+    with torch.no_grad():
+        feat = gen.gen_feature(lq_d)
+    ms_head, _, _ = timed(lambda: gen.query_rgb(feat, coord_d, cell_d, lr_image=lq_d, eval_bsize=EVAL_BSIZE), args.steps)
+    ms_enc, _, _ = timed(lambda: gen.gen_feature(lq_d), args.steps)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        from oracle.ciaosr_oracle import cross_scale_flops, head_flops_per_query
+        pk = peaks()
+        engine = "tcgen05" if gen.head_plan().engine_supported("tcgen05") and args.engine != "simt" else "simt"
+        pair_ms = stages["pair_mlp"][0] / args.steps
+        pair_launches = max(1, stages["pair_mlp"][1] // args.steps)
+        fl_head = head_flops_per_query(C)                      # 8 865 280
+        fl_q = 2 * (640 * 256 + 3 * 256 * 256 + 256 * 3)       # imnet_q share, not in the pair stage
+        fl_pair = (fl_head - fl_q) * npx
+        achieved = fl_pair / (pair_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "pair_mlp stage (%d launches/step)" % pair_launches,
+                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                "peak_source": pk["source"] + ", sustained dense bf16",
+                "algorithmic_flops_per_px": fl_head - fl_q, "ms_per_step": pair_ms,
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+                "hbm_algorithmic_GBps": 61.0 * npx / (ms_head * 1e-3) / 1e9, "hbm_peak_GBps": pk["hbm_gbs"]}
+        line = {
+            "metric": METRIC, "value": world * npx / (ms_step * 1e-3) / 1e6, "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "RDN-CiaoSR config 001 (RDN 16x8 g64, imnet 256x4, cs_attn), "
+                                   "batch 16 of 48x48 LR -> x4, per GPU",
+                       "px_per_step_per_gpu": npx, "eval_bsize": EVAL_BSIZE, "engine": engine,
+                       "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB",
+                       "head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
+                       "head_ms": ms_head, "encoder_ms": ms_enc,
+                       "encoder": "PyTorch RDN fp32 (cudnn.allow_tf32=%s)" % torch.backends.cudnn.allow_tf32},
+            "clocks": clocks,
+            "e2e": {"value": world * npx / (ms_e2e * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            val, ms = cpu_reference_sample(2, 1, threads)
+            line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
+                                    "sample": "1 of the 16 crops (36 864 px), 2 timed runs, %.0f ms each" % ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

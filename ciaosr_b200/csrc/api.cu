@@ -1,0 +1,299 @@
+// C ABI of libciaosr_b200.so (see include/ciaosr_b200.h for the contract).
+#include "kernels.cuh"
+#include "pairs.cuh"
+#include <mutex>
+#include <vector>
+
+namespace ciaosr {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- stage timing -------------------------------------------------------------
+struct StageRec { int stage; cudaEvent_t a, b; long long launches; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<StageRec> g_prof;
+
+StageScope::StageScope(int stage_, cudaStream_t st_) : stage(stage_), st(st_), a(nullptr), b(nullptr) {
+  on = g_prof_on.load() != 0;
+  if (!on) return;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+  cudaEventRecord(a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(StageRec{stage, a, b, g_launch_count.load()});
+}
+StageScope::~StageScope() {
+  if (!on) return;
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
+    if (it->b == b) { it->launches = g_launch_count.load() - it->launches; break; }
+}
+
+static int check_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return CIAOSR_E_NO_DEVICE;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+    return CIAOSR_E_NO_DEVICE;
+  }
+  return CIAOSR_OK;
+}
+
+static int pick_engine(const PlanLayout& L, int engine, int* out) {
+  if (engine == CIAOSR_ENGINE_AUTO) engine = L.tc_ok ? CIAOSR_ENGINE_TCGEN05 : CIAOSR_ENGINE_SIMT;
+  CIAOSR_REQUIRE(engine == CIAOSR_ENGINE_SIMT || engine == CIAOSR_ENGINE_TCGEN05, CIAOSR_E_INVALID,
+                 "unknown engine %d", engine);
+  CIAOSR_REQUIRE(engine != CIAOSR_ENGINE_TCGEN05 || L.tc_ok, CIAOSR_E_INVALID,
+                 "tcgen05 engine needs C %% 16 == 0, local_size == 2 and three MLPs with hidden_list "
+                 "[256,256,256,256]; use CIAOSR_ENGINE_SIMT for this configuration");
+  *out = engine;
+  return CIAOSR_OK;
+}
+
+struct CallLayout {     // workspace carve-up shared by workspace_bytes and the forward
+  float* featT; float* nlT; void* rest; size_t rest_bytes; size_t total;
+};
+
+static size_t engine_ws(const PlanLayout& L, int engine, int B, int H, int W, int Q) {
+  return engine == CIAOSR_ENGINE_TCGEN05 ? head_tc_workspace(L, B, H, W, Q)
+                                          : head_simt_workspace(L, B, H, W, Q);
+}
+
+static CallLayout carve_call(const PlanLayout& L, int engine, int B, int H, int W, int Q, void* ws,
+                             size_t ws_bytes) {
+  Arena a(ws, ws ? ws_bytes : 0);
+  CallLayout c;
+  c.featT = a.take<float>((size_t)B * H * W * L.C);
+  c.nlT = a.take<float>((size_t)B * H * W * (L.Cn > 0 ? L.Cn : 1));
+  size_t inner = engine_ws(L, engine, B, H, W, Q);
+  if (L.non_local) {
+    const size_t csa = cs_attn_workspace(L, H, W);
+    inner = inner > csa ? inner : csa;
+  }
+  c.rest = a.take<char>(inner);
+  c.rest_bytes = inner;
+  c.total = a.used();
+  return c;
+}
+
+}  // namespace ciaosr
+
+using namespace ciaosr;
+
+extern "C" {
+
+const char* ciaosr_last_error(void) { return g_err; }
+int ciaosr_abi_version(void) { return CIAOSR_ABI_VERSION; }
+long long ciaosr_launch_count(void) { return g_launch_count.load(); }
+
+int ciaosr_engine_supported(const ciaosr_head_desc* desc, int engine) {
+  PlanLayout L;
+  int rc = plan_layout(desc, &L);
+  if (rc) return rc;
+  if (engine == CIAOSR_ENGINE_SIMT || engine == CIAOSR_ENGINE_AUTO) return 1;
+  if (engine == CIAOSR_ENGINE_TCGEN05) return L.tc_ok ? 1 : 0;
+  return 0;
+}
+
+int ciaosr_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return CIAOSR_OK;
+}
+
+int ciaosr_profile_read(float* ms, int* launches, int n) {
+  CIAOSR_REQUIRE(ms != nullptr && n >= CIAOSR_N_STAGES, CIAOSR_E_INVALID,
+                 "ms must hold CIAOSR_N_STAGES floats");
+  std::vector<StageRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  for (auto& r : recs) {
+    float t = 0.0f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess &&
+        r.stage >= 0 && r.stage < n) {
+      ms[r.stage] += t;
+      if (launches) launches[r.stage] += (int)r.launches;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  return CIAOSR_OK;
+}
+
+int ciaosr_plan_bytes(const ciaosr_head_desc* desc, size_t* bytes) {
+  CIAOSR_REQUIRE(bytes != nullptr, CIAOSR_E_INVALID, "bytes is NULL");
+  PlanLayout L;
+  int rc = plan_layout(desc, &L);
+  if (rc) return rc;
+  *bytes = L.total_floats * sizeof(float);
+  return CIAOSR_OK;
+}
+
+int ciaosr_plan_init(const ciaosr_head_desc* desc, void* plan, size_t plan_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PlanLayout L;
+  if ((rc = plan_layout(desc, &L))) return rc;
+  CIAOSR_REQUIRE(plan != nullptr && ((uintptr_t)plan % 256) == 0, CIAOSR_E_WORKSPACE,
+                 "plan buffer must be a 256-byte aligned device pointer");
+  CIAOSR_REQUIRE(plan_bytes >= L.total_floats * sizeof(float), CIAOSR_E_WORKSPACE,
+                 "plan buffer too small: need %zu, have %zu", L.total_floats * sizeof(float), plan_bytes);
+  return plan_pack(desc, L, (float*)plan, (cudaStream_t)stream);
+}
+
+int ciaosr_workspace_bytes(const ciaosr_head_desc* desc, int B, int H, int W, int q, int engine,
+                           size_t* bytes) {
+  CIAOSR_REQUIRE(bytes != nullptr, CIAOSR_E_INVALID, "bytes is NULL");
+  CIAOSR_REQUIRE(B > 0 && H > 0 && W > 0 && q >= 0, CIAOSR_E_INVALID, "bad shape B=%d H=%d W=%d q=%d",
+                 B, H, W, q);
+  PlanLayout L;
+  int rc = plan_layout(desc, &L);
+  if (rc) return rc;
+  int eng;
+  if ((rc = pick_engine(L, engine, &eng))) return rc;
+  *bytes = carve_call(L, eng, B, H, W, q, nullptr, 0).total;
+  return CIAOSR_OK;
+}
+
+int ciaosr_cross_scale_attn_forward(const ciaosr_head_desc* desc, const void* plan,
+                                    const float* feature, int B, int H, int W, float* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PlanLayout L;
+  if ((rc = plan_layout(desc, &L))) return rc;
+  CIAOSR_REQUIRE(L.non_local, CIAOSR_E_INVALID, "desc.non_local_attn is 0: no cross-scale attention");
+  CIAOSR_REQUIRE(plan && feature && out, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(B > 0 && H > 0 && W > 0, CIAOSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a(workspace, workspace_bytes);
+  float* featT = a.take<float>((size_t)B * H * W * L.C);
+  const size_t inner = cs_attn_workspace(L, H, W);
+  void* rest = a.take<char>(inner);
+  CIAOSR_REQUIRE(workspace && a.ok, CIAOSR_E_WORKSPACE, "workspace too small: need %zu, have %zu",
+                 a.used(), workspace_bytes);
+  if ((rc = transpose_batched(feature, featT, B, L.C, H * W, st))) return rc;
+  return run_cs_attn(L, (const float*)plan, featT, B, H, W, nullptr, 0, out, rest, inner, st);
+}
+
+int ciaosr_query_rgb_forward(const ciaosr_head_desc* desc, const void* plan, const float* feature,
+                             const float* nonlocal, const float* coord, const float* cell,
+                             const float* lr_image, int B, int H, int W, int q, int eval_bsize,
+                             int engine, float* out, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  PlanLayout L;
+  if ((rc = plan_layout(desc, &L))) return rc;
+  CIAOSR_REQUIRE(plan && feature && coord && cell && out, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(B > 0 && H > 0 && W > 0 && q >= 0, CIAOSR_E_INVALID, "bad shape B=%d H=%d W=%d q=%d",
+                 B, H, W, q);
+  CIAOSR_REQUIRE((long long)B * H * W * 9 < (1LL << 31) && (long long)B * q < (1LL << 40),
+                 CIAOSR_E_INVALID, "problem too large for 32-bit pixel indices");
+  if (q == 0) return CIAOSR_OK;
+  int eng;
+  if ((rc = pick_engine(L, engine, &eng))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CallLayout c = carve_call(L, eng, B, H, W, q, workspace, workspace_bytes);
+  CIAOSR_REQUIRE(workspace && c.total <= workspace_bytes && ((uintptr_t)workspace % 256) == 0,
+                 CIAOSR_E_WORKSPACE, "workspace too small or misaligned: need %zu, have %zu", c.total,
+                 workspace_bytes);
+  {
+    StageScope sc(0, st);
+    if ((rc = transpose_batched(feature, c.featT, B, L.C, H * W, st))) return rc;
+    if (L.non_local && nonlocal) {
+      if ((rc = transpose_batched(nonlocal, c.nlT, B, L.Cn, H * W, st))) return rc;
+    }
+  }
+  if (L.non_local && !nonlocal) {
+    StageScope sc(1, st);
+    if ((rc = run_cs_attn(L, (const float*)plan, c.featT, B, H, W, c.nlT, L.Cn, nullptr, c.rest,
+                          c.rest_bytes, st))) return rc;
+  }
+  HeadArgs a;
+  a.B = B; a.H = H; a.W = W; a.Q = q; a.eval_bsize = eval_bsize;
+  a.featT = c.featT; a.nlT = L.non_local ? c.nlT : nullptr;
+  a.coord = coord; a.cell = cell; a.lr = lr_image; a.out = out;
+  // make_coord: seq_i = (-1 + 1/n) + (2/n) * i, constants formed in double (python floats)
+  a.cy0 = (float)(-1.0 + 1.0 / H); a.cy1 = (float)(2.0 * (1.0 / H));
+  a.cx0 = (float)(-1.0 + 1.0 / W); a.cx1 = (float)(2.0 * (1.0 / W));
+  if (eng == CIAOSR_ENGINE_TCGEN05)
+    return run_head_tc(L, (const float*)plan, a, c.rest, c.rest_bytes, st);
+  return run_head_simt(L, (const float*)plan, a, c.rest, c.rest_bytes, st);
+}
+
+// ---- tiled-inference epilogue ---------------------------------------------------------
+__global__ void tile_blend_acc_kernel(const float* __restrict__ pred, int th, int tw,
+                                      float* __restrict__ acc, float* __restrict__ cnt, int Ho,
+                                      int Wo, int y0, int x0, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % 3);
+  const long long p = i / 3;
+  const int x = (int)(p % tw), y = (int)((p / tw) % th), b = (int)(p / ((long long)tw * th));
+  const long long o = (((long long)b * 3 + ch) * Ho + (y0 + y)) * Wo + (x0 + x);
+  acc[o] += pred[i];
+  cnt[o] += 1.0f;
+}
+
+__global__ void tile_blend_finish_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
+                                         int HoWo, const float* __restrict__ mean,
+                                         const float* __restrict__ stdv, int clamp01,
+                                         float* __restrict__ out, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % 3);
+  const long long p = i / 3;
+  const long long pix = p % HoWo, b = p / HoWo;
+  float v = __fdiv_rn(acc[(b * 3 + ch) * HoWo + pix], cnt[(b * 3 + ch) * HoWo + pix]);
+  if (mean) v = __fadd_rn(__fmul_rn(v, stdv[ch]), mean[ch]);
+  if (clamp01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+  out[i] = v;
+}
+
+int ciaosr_tile_blend_accumulate(const float* tile_pred, int B, int th, int tw, float* acc, float* cnt,
+                                 int Ho, int Wo, int y0, int x0, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  CIAOSR_REQUIRE(tile_pred && acc && cnt, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + th <= Ho && x0 + tw <= Wo, CIAOSR_E_INVALID,
+                 "tile (%d,%d)+(%d,%d) outside the %dx%d canvas", y0, x0, th, tw, Ho, Wo);
+  const long long total = 3LL * B * th * tw;
+  if (total == 0) return CIAOSR_OK;
+  CIAOSR_LAUNCH(tile_blend_acc_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream, tile_pred, th,
+                tw, acc, cnt, Ho, Wo, y0, x0, total);
+  return CIAOSR_OK;
+}
+
+int ciaosr_tile_blend_finish(const float* acc, const float* cnt, int B, int Ho, int Wo,
+                             const float* mean3, const float* std3, int clamp01, float* out,
+                             void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  CIAOSR_REQUIRE(acc && cnt && out, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE((mean3 == nullptr) == (std3 == nullptr), CIAOSR_E_INVALID,
+                 "mean3 and std3 must be given together");
+  const long long total = 3LL * B * Ho * Wo;
+  if (total == 0) return CIAOSR_OK;
+  CIAOSR_LAUNCH(tile_blend_finish_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream, acc, cnt,
+                Ho * Wo, mean3, std3, clamp01, out, total);
+  return CIAOSR_OK;
+}
+
+}  // extern "C"

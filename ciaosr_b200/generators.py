@@ -1,0 +1,196 @@
+"""The drop-in boundary: the reference's generator classes over the native head.
+
+Mirrors ``LocalImplicitSRNet`` and its RDN / EDSR / SwinIR subclasses
+(mmedited/models/backbones/sr_backbones/ciaosr_net.py:17-525): same constructor
+keywords (plus the six keywords the 002 configs pass),
+same ``state_dict`` keys, same ``forward(x, coord, cell, test_mode)`` ->
+``[B, Q, 3]``, same ``init_weights(pretrained, strict)`` error behaviour.
+
+What differs is where the work happens: ``gen_feature`` (the encoder) stays in
+PyTorch; everything after it -- unfold, cross-scale attention, local-ensemble
+encoding, the three MLPs, inner attention, bilinear residual -- is one call
+into ``libciaosr_b200.so``.  There is no PyTorch/CPU fallback for that part.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import native
+from .builder import build_backbone, build_component, load_checkpoint
+from .cross_scale_attention import CrossScaleAttention
+
+
+class LocalImplicitSRNet(nn.Module):
+    """Base generator (ciaosr_net.py:17-264).
+
+    Args follow the reference; ``engine`` ('auto' | 'simt' | 'tcgen05') selects the
+    native engine and is the only addition.
+    """
+
+    def __init__(self, encoder, imnet_q, imnet_k, imnet_v, query_mlp=None, key_mlp=None,
+                 value_mlp=None, local_size=2, feat_unfold=True, eval_bsize=None,
+                 non_local_attn=True, multi_scale=[2], softmax_scale=1,
+                 # keywords the 002 configs pass (configs/002_real_wogan...py:54-59)
+                 local_ensemble_coord=True, imnet_k_type=None, imnet_v_type=None, res=True,
+                 cat_nla_v=None, engine="auto"):
+        super().__init__()
+        self.feat_unfold = feat_unfold
+        self.eval_bsize = eval_bsize
+        self.local_size = local_size
+        self.non_local_attn = non_local_attn
+        self.multi_scale = list(multi_scale)
+        self.softmax_scale = softmax_scale
+        self.res = res
+        self.engine = engine
+        if not local_ensemble_coord:
+            raise NotImplementedError("local_ensemble_coord=False has no counterpart in the reference head")
+
+        self.encoder = build_backbone(encoder)
+        imnet_dim = self.encoder.mid_channels if hasattr(self.encoder, "mid_channels") \
+            else self.encoder.embed_dim
+        self.imnet_dim = imnet_dim
+        # the reference mutates the config dicts in place (ciaosr_net.py:61-76); so do we
+        unit = imnet_dim * 9 if feat_unfold else imnet_dim
+        imnet_q["in_dim"] = unit
+        imnet_k["in_dim"] = imnet_k["out_dim"] = unit
+        imnet_v["in_dim"] = imnet_v["out_dim"] = unit
+        imnet_k["in_dim"] += 4
+        imnet_v["in_dim"] += 4
+        if non_local_attn:
+            extra = imnet_dim * len(self.multi_scale)
+            imnet_q["in_dim"] += extra
+            imnet_v["in_dim"] += extra
+            imnet_v["out_dim"] += extra
+        self.imnet_q = build_component(imnet_q)
+        self.imnet_k = build_component(imnet_k)
+        self.imnet_v = build_component(imnet_v)
+        if non_local_attn:
+            self.cs_attn = CrossScaleAttention(channel=imnet_dim, scale=self.multi_scale)
+        self._plan = None
+        self._plan_key = None
+
+    # -- native plan -----------------------------------------------------------------
+    def _head_params(self):
+        prefixes = ("imnet_q.", "imnet_k.", "imnet_v.", "cs_attn.")
+        return {k: v for k, v in self.state_dict().items() if k.startswith(prefixes)}
+
+    def head_plan(self):
+        """Packed weights for the kernels; rebuilt when a parameter changes or moves."""
+        params = self._head_params()
+        key = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in params.items())
+        if self._plan is None or key != self._plan_key:
+            self._plan = native.HeadPlan(
+                params, self.imnet_dim, local_size=self.local_size,
+                non_local_attn=self.non_local_attn, multi_scale=self.multi_scale,
+                softmax_scale=float(self.softmax_scale), feat_unfold=self.feat_unfold,
+                cs_softmax_scale=float(self.cs_attn.softmax_scale) if self.non_local_attn else 10.0)
+            self._plan_key = key
+        return self._plan
+
+    # -- reference API -----------------------------------------------------------------
+    def forward(self, x, coord, cell, test_mode=False):
+        """x [B,3,H,W] normalised LR, coord/cell [B,Q,2] (y,x) -> [B,Q,3]."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not test_mode:
+            raise NotImplementedError(
+                "ciaosr_b200 implements the inference forward of the head only; run training "
+                "forwards under torch.no_grad() or with test_mode=True (SURVEY.md 8f #4)")
+        with torch.no_grad():
+            feature = self.gen_feature(x)
+            chunk = self.eval_bsize if (self.eval_bsize is not None and test_mode) else None
+            return self.query_rgb(feature, coord, cell, lr_image=x if self.res else None,
+                                  eval_bsize=chunk)
+
+    def query_rgb(self, features, coord, scale=None, lr_image=None, eval_bsize=None):
+        """ciaosr_net.py:113-224 (`scale` is the reference's name for the cell tensor)."""
+        if not isinstance(features, (list, tuple)):
+            features = [features]
+        if len(features) != 1:
+            raise NotImplementedError("every reference encoder returns exactly one feature map")
+        return self.head_plan().query_rgb(features[0], coord, scale, lr_image=lr_image,
+                                          eval_bsize=eval_bsize, engine=self.engine)
+
+    def batched_predict(self, x, coord, cell):
+        """ciaosr_net.py:226-248.  The native call handles the whole query axis at once;
+        `eval_bsize` only selects which cell seeds tx/ty, exactly like the chunk loop."""
+        return self.query_rgb(x, coord, cell, eval_bsize=self.eval_bsize)
+
+    def init_weights(self, pretrained=None, strict=True):
+        if isinstance(pretrained, str):
+            load_checkpoint(self, pretrained, strict=strict)
+        elif pretrained is not None:
+            raise TypeError('"pretrained" must be a str or None. '
+                            f'But received {type(pretrained)}.')
+
+    def gen_feature(self, x):
+        raise NotImplementedError
+
+
+class LocalImplicitSRRDN(LocalImplicitSRNet):
+    """ciaosr_net.py:267-342."""
+
+    def __init__(self, encoder, imnet_q, imnet_k, imnet_v, **kwargs):
+        super().__init__(encoder=encoder, imnet_q=imnet_q, imnet_k=imnet_k, imnet_v=imnet_v, **kwargs)
+        self.sfe1 = self.encoder.sfe1
+        self.sfe2 = self.encoder.sfe2
+        self.rdbs = self.encoder.rdbs
+        self.gff = self.encoder.gff
+        self.num_blocks = self.encoder.num_blocks
+        del self.encoder
+
+    def gen_feature(self, x):
+        sfe1 = self.sfe1(x)
+        x = self.sfe2(sfe1)
+        local_features = []
+        for i in range(self.num_blocks):
+            x = self.rdbs[i](x)
+            local_features.append(x)
+        return [self.gff(torch.cat(local_features, 1)) + sfe1]
+
+
+class LocalImplicitSREDSR(LocalImplicitSRNet):
+    """ciaosr_net.py:345-408."""
+
+    def __init__(self, encoder, imnet_q, imnet_k, imnet_v, **kwargs):
+        super().__init__(encoder=encoder, imnet_q=imnet_q, imnet_k=imnet_k, imnet_v=imnet_v, **kwargs)
+        self.conv_first = self.encoder.conv_first
+        self.body = self.encoder.body
+        self.conv_after_body = self.encoder.conv_after_body
+        del self.encoder
+
+    def gen_feature(self, x):
+        x = self.conv_first(x)
+        res = self.conv_after_body(self.body(x))
+        res += x
+        return [res]
+
+
+class LocalImplicitSRSWINIR(LocalImplicitSRNet):
+    """ciaosr_net.py:411-525."""
+
+    def __init__(self, window_size, encoder, imnet_q, imnet_k, imnet_v, **kwargs):
+        super().__init__(encoder=encoder, imnet_q=imnet_q, imnet_k=imnet_k, imnet_v=imnet_v, **kwargs)
+        self.window_size = window_size
+        self.conv_first = self.encoder.conv_first
+        self.patch_embed = self.encoder.patch_embed
+        self.pos_drop = self.encoder.pos_drop
+        self.layers = self.encoder.layers
+        self.norm = self.encoder.norm
+        self.patch_unembed = self.encoder.patch_unembed
+        self.conv_after_body = self.encoder.conv_after_body
+        del self.encoder
+
+    def forward_features(self, x):
+        x_size = (x.shape[2], x.shape[3])
+        x = self.pos_drop(self.patch_embed(x))
+        for layer in self.layers:
+            x = layer(x, x_size)
+        return self.patch_unembed(self.norm(x), x_size)
+
+    def gen_feature(self, img):
+        _, _, h, w = img.size()
+        pad_h = (self.window_size - h % self.window_size) % self.window_size
+        pad_w = (self.window_size - w % self.window_size) % self.window_size
+        x = self.conv_first(F.pad(img, (0, pad_w, 0, pad_h), "reflect"))
+        res = self.conv_after_body(self.forward_features(x))
+        res += x
+        return [res[:, :, :h, :w]]

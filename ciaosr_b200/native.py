@@ -1,0 +1,234 @@
+"""Host-side driver of the C ABI: descriptors, plan caching, workspace, calls.
+
+PyTorch is used here only as plumbing: it owns device memory (plan buffer,
+workspace, outputs) and provides the current CUDA stream.  All arithmetic of
+the hot path happens inside ``libciaosr_b200.so``.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CiaoSRNativeError, ENGINES  # noqa: F401  (re-exported)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: ciaosr_b200 has no CPU path for the head")
+    return t.contiguous()
+
+
+def _mlp_desc(layers, keep):
+    """layers: list of (weight[out,in], bias[out]) tensors."""
+    d = _lib.MlpDesc()
+    if len(layers) > _lib.MAX_LAYERS:
+        raise ValueError(f"MLP with {len(layers)} Linear layers exceeds CIAOSR_MAX_LAYERS")
+    d.n_layers = len(layers)
+    for i, (w, b) in enumerate(layers):
+        w, b = _f32c(w.detach(), "weight"), _f32c(b.detach(), "bias")
+        keep += [w, b]
+        if i == 0:
+            d.dims[0] = w.shape[1]
+        elif w.shape[1] != d.dims[i]:
+            raise ValueError(f"layer {i} expects {w.shape[1]} inputs, previous layer gives {d.dims[i]}")
+        d.dims[i + 1] = w.shape[0]
+        d.weight[i] = w.data_ptr()
+        d.bias[i] = b.data_ptr()
+    return d
+
+
+class HeadPlan:
+    """Weights of one head, packed on the device for the kernels.
+
+    `params` maps the reference's state_dict key names (relative to the
+    generator) to tensors, e.g. ``imnet_k.layers.0.weight``,
+    ``cs_attn.conv_match_1.1.weight``.
+    """
+
+    def __init__(self, params, channels, local_size=2, non_local_attn=True, multi_scale=(2,),
+                 softmax_scale=1.0, feat_unfold=True, cs_softmax_scale=10.0):
+        lib = _lib.load()
+        self._keep = []
+        self.device = params["imnet_q.layers.0.weight"].device
+        if self.device.type != "cuda":
+            raise RuntimeError("HeadPlan needs CUDA parameters: ciaosr_b200 has no CPU path for the head")
+        d = _lib.HeadDesc()
+        d.abi_version = _lib.ABI_VERSION
+        d.channels = int(channels)
+        d.feat_unfold = 1 if feat_unfold else 0
+        d.local_size = int(local_size)
+        d.non_local_attn = 1 if non_local_attn else 0
+        d.softmax_scale = float(softmax_scale)
+        for name in ("imnet_q", "imnet_k", "imnet_v"):
+            layers, i = [], 0
+            while f"{name}.layers.{i}.weight" in params:
+                layers.append((params[f"{name}.layers.{i}.weight"], params[f"{name}.layers.{i}.bias"]))
+                i += 2
+            setattr(d, name, _mlp_desc(layers, self._keep))
+        if non_local_attn:
+            a = d.cs_attn
+            a.channels = int(channels)
+            a.n_scales = len(multi_scale)
+            if len(multi_scale) > _lib.MAX_SCALES:
+                raise ValueError("too many scales")
+            for i, s in enumerate(multi_scale):
+                a.scales[i] = int(s)
+            a.softmax_scale = float(cs_softmax_scale)
+
+            def p(key):
+                t = _f32c(params[f"cs_attn.{key}"].detach(), key)
+                self._keep.append(t)
+                return t.data_ptr()
+
+            a.match1_w, a.match1_b, a.match1_slope = p("conv_match_1.0.weight"), p("conv_match_1.0.bias"), p("conv_match_1.1.weight")
+            a.match2_w, a.match2_b, a.match2_slope = p("conv_match_2.0.weight"), p("conv_match_2.0.bias"), p("conv_match_2.1.weight")
+            a.assembly_w, a.assembly_b, a.assembly_slope = p("conv_assembly.0.weight"), p("conv_assembly.0.bias"), p("conv_assembly.1.weight")
+            a.down_w, a.down_b = p("down.weight"), p("down.bias")
+            a.escape_nan = p("escape_NaN")
+        self.desc = d
+        self.channels = int(channels)
+        self.n_nonlocal = int(channels) * len(multi_scale) if non_local_attn else 0
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.ciaosr_plan_bytes(ctypes.byref(d), ctypes.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.buf = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.ciaosr_plan_init(ctypes.byref(d), _ptr(self.buf), nbytes.value,
+                                            _stream(self.device)))
+        self._ws = None
+
+    # -- workspace (grown on demand, reused across calls on the same stream) ----
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def workspace_bytes(self, B, H, W, q, engine="auto"):
+        n = ctypes.c_size_t(0)
+        _lib.check(_lib.load().ciaosr_workspace_bytes(ctypes.byref(self.desc), B, H, W, q,
+                                                      ENGINES[engine], ctypes.byref(n)))
+        return n.value
+
+    def engine_supported(self, engine):
+        return _lib.load().ciaosr_engine_supported(ctypes.byref(self.desc), ENGINES[engine]) == 1
+
+    # -- calls ---------------------------------------------------------------------
+    def cross_scale_attention(self, feature):
+        """feature [B,C,H,W] -> [B,Cn,H,W] (CrossScaleAttention.forward)."""
+        feature = _f32c(feature, "feature")
+        B, C, H, W = feature.shape
+        if C != self.channels:
+            raise ValueError(f"feature has {C} channels, head was built for {self.channels}")
+        out = torch.empty(B, self.n_nonlocal, H, W, dtype=torch.float32, device=feature.device)
+        nbytes = self.workspace_bytes(B, H, W, 0, "simt")
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ciaosr_cross_scale_attn_forward(
+                ctypes.byref(self.desc), _ptr(self.buf), _ptr(feature), B, H, W, _ptr(out),
+                _ptr(ws), ws.numel(), _stream(self.device)))
+        return out
+
+    def query_rgb(self, feature, coord, cell, lr_image=None, nonlocal_feat=None, eval_bsize=None,
+                  engine="auto"):
+        """The head: feature [B,C,H,W], coord/cell [B,q,2] -> [B,q,3]."""
+        feature = _f32c(feature, "feature")
+        coord, cell = _f32c(coord, "coord"), _f32c(cell, "cell")
+        B, C, H, W = feature.shape
+        if C != self.channels:
+            raise ValueError(f"feature has {C} channels, head was built for {self.channels}")
+        if coord.dim() != 3 or coord.shape[-1] != 2 or coord.shape[0] != B:
+            raise ValueError(f"coord must be [B,q,2] with B={B}, got {tuple(coord.shape)}")
+        if cell.shape != coord.shape:
+            raise ValueError(f"cell {tuple(cell.shape)} and coord {tuple(coord.shape)} differ")
+        q = coord.shape[1]
+        if lr_image is not None:
+            lr_image = _f32c(lr_image, "lr_image")
+            if tuple(lr_image.shape) != (B, 3, H, W):
+                raise ValueError(f"lr_image must be [{B},3,{H},{W}], got {tuple(lr_image.shape)}")
+        if nonlocal_feat is not None:
+            nonlocal_feat = _f32c(nonlocal_feat, "nonlocal_feat")
+            if tuple(nonlocal_feat.shape) != (B, self.n_nonlocal, H, W):
+                raise ValueError("nonlocal_feat has the wrong shape")
+        out = torch.empty(B, q, 3, dtype=torch.float32, device=feature.device)
+        nbytes = self.workspace_bytes(B, H, W, q, engine)
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ciaosr_query_rgb_forward(
+                ctypes.byref(self.desc), _ptr(self.buf), _ptr(feature), _ptr(nonlocal_feat),
+                _ptr(coord), _ptr(cell), _ptr(lr_image), B, H, W, q,
+                int(eval_bsize) if eval_bsize else 0, ENGINES[engine], _ptr(out), _ptr(ws),
+                ws.numel(), _stream(self.device)))
+        return out
+
+
+def tile_blend_accumulate(tile_pred, acc, cnt, y0, x0, th, tw):
+    """acc/cnt [B,3,Ho,Wo] += tile_pred [B, th*tw, 3] at (y0, x0) (ciaosr.py:253-255)."""
+    tile_pred = _f32c(tile_pred, "tile_pred")
+    B = tile_pred.shape[0]
+    Ho, Wo = acc.shape[-2:]
+    with torch.cuda.device(acc.device):
+        _lib.check(_lib.load().ciaosr_tile_blend_accumulate(
+            _ptr(tile_pred), B, th, tw, _ptr(acc), _ptr(cnt), Ho, Wo, y0, x0, _stream(acc.device)))
+
+
+def tile_blend_finish(acc, cnt, mean=None, std=None, clamp01=False):
+    """[B,3,Ho,Wo] accumulators -> [B, Ho*Wo, 3] = acc/cnt (* std + mean, clamped)."""
+    B, _, Ho, Wo = acc.shape
+    out = torch.empty(B, Ho * Wo, 3, dtype=torch.float32, device=acc.device)
+    mean = _f32c(mean.reshape(3), "mean") if mean is not None else None
+    std = _f32c(std.reshape(3), "std") if std is not None else None
+    with torch.cuda.device(acc.device):
+        _lib.check(_lib.load().ciaosr_tile_blend_finish(
+            _ptr(acc), _ptr(cnt), B, Ho, Wo, _ptr(mean), _ptr(std), 1 if clamp01 else 0, _ptr(out),
+            _stream(acc.device)))
+    return out
+
+
+def profile_enable(on=True):
+    """Bracket the library's stages with CUDA events (see ciaosr_profile_read)."""
+    _lib.check(_lib.load().ciaosr_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{stage: (milliseconds, launches)} accumulated since the last read; synchronises."""
+    ms = (ctypes.c_float * _lib.N_STAGES)()
+    n = (ctypes.c_int * _lib.N_STAGES)()
+    _lib.check(_lib.load().ciaosr_profile_read(ms, n, _lib.N_STAGES))
+    return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_lib.STAGE_NAMES)}
+
+
+def launch_count():
+    return int(_lib.load().ciaosr_launch_count())
+
+
+class CsAttnOnlyPlan(HeadPlan):
+    """A plan for calling CrossScaleAttention as a standalone module.
+
+    The C ABI describes a whole head; the three MLPs are filled with 1-wide
+    zero layers that are never executed by ``cross_scale_attention``.
+    """
+
+    def __init__(self, params, channels, multi_scale=(2,), cs_softmax_scale=10.0):
+        dev = params["cs_attn.down.weight"].device
+        dk, cn = 9 * channels, channels * len(multi_scale)
+        dv = dk + cn
+        full = dict(params)
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=torch.float32, device=dev)
+
+        for name, din, dout in (("imnet_k", dk + 4, dk), ("imnet_v", dv + 4, dv), ("imnet_q", dv, 3)):
+            full[f"{name}.layers.0.weight"], full[f"{name}.layers.0.bias"] = zeros(1, din), zeros(1)
+            full[f"{name}.layers.2.weight"], full[f"{name}.layers.2.bias"] = zeros(dout, 1), zeros(dout)
+        super().__init__(full, channels, local_size=2, non_local_attn=True, multi_scale=multi_scale,
+                         softmax_scale=1.0, cs_softmax_scale=cs_softmax_scale)

@@ -1,0 +1,140 @@
+"""Restorer (mmedit "model") level of the boundary: ``CiaoSR`` as the reference's
+configs build it (mmedited/models/restorers/ciaosr.py:17-258 on top of
+basic_restorer.py:16-124).  Inference side only: ``forward(test_mode=True)``,
+``forward_test``, ``clip_test``, ``evaluate``.  The generator call inside is the
+drop-in boundary; the tile blend + de-normalise + clamp epilogue runs in two small
+native kernels instead of the reference's Python double loop over full-frame masks.
+"""
+import math
+import numbers
+import os.path as osp
+
+import torch
+import torch.nn as nn
+
+from . import native
+from .builder import build_backbone, build_loss
+from .coords import make_coord
+from .metrics import psnr, ssim, tensor2img
+
+
+class BasicRestorer(nn.Module):
+    allowed_metrics = {"PSNR": psnr, "SSIM": ssim}
+
+    def __init__(self, generator, pixel_loss, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__()
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.fp16_enabled = False
+        self.generator = build_backbone(generator)
+        self.init_weights(pretrained)
+        self.pixel_loss = build_loss(pixel_loss)
+
+    def init_weights(self, pretrained=None):
+        self.generator.init_weights(pretrained)
+
+    def forward(self, lq, gt=None, test_mode=False, **kwargs):
+        if test_mode:
+            return self.forward_test(lq, gt, **kwargs)
+        raise NotImplementedError("training forward is out of scope for ciaosr_b200 (SURVEY.md 8f #4)")
+
+    def evaluate(self, output, gt):
+        """basic_restorer.py:101-124: metrics on uint8 images with crop_border / convert_to."""
+        crop_border = self.test_cfg["crop_border"]
+        convert_to = self.test_cfg.get("convert_to", None)
+        output, gt = tensor2img(output), tensor2img(gt)
+        return {m: self.allowed_metrics[m](output, gt, crop_border, convert_to=convert_to)
+                for m in self.test_cfg["metrics"]}
+
+
+class CiaoSR(BasicRestorer):
+    def __init__(self, generator, pixel_loss, rgb_mean=(0.5, 0.5, 0.5), rgb_std=(0.5, 0.5, 0.5),
+                 train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__(generator, pixel_loss, train_cfg=train_cfg, test_cfg=test_cfg,
+                         pretrained=pretrained)
+        rgb_mean, rgb_std = torch.FloatTensor(rgb_mean), torch.FloatTensor(rgb_std)
+        self.lq_mean, self.lq_std = rgb_mean.view(1, -1, 1, 1), rgb_std.view(1, -1, 1, 1)
+        self.gt_mean, self.gt_std = rgb_mean.view(1, 1, -1), rgb_std.view(1, 1, -1)
+
+    def forward_test(self, lq, gt=None, coord=None, cell=None, meta=None, save_image=False,
+                     save_path=None, iteration=None):
+        """ciaosr.py:111-203."""
+        self.lq_mean, self.lq_std = self.lq_mean.to(lq), self.lq_std.to(lq)
+        lq = (lq - self.lq_mean) / self.lq_std
+        self.gt_mean, self.gt_std = self.gt_mean.to(lq), self.gt_std.to(lq)
+        with torch.no_grad():
+            if self.test_cfg is not None and self.test_cfg.get("tile", None):
+                pred = self.clip_test(lq, self.generator, denorm=True)
+            else:
+                pred = self.generator(lq, coord, cell, test_mode=True)
+                pred = pred * self.gt_std + self.gt_mean
+                pred.clamp_(0, 1)
+        ih, iw = lq.shape[-2:]
+        if coord is not None:
+            s = math.sqrt(coord.shape[1] / (ih * iw))
+        else:
+            s = self.test_cfg["scale"]
+        shape = [lq.shape[0], round(ih * s), round(iw * s), 3]
+        pred = pred.view(*shape).permute(0, 3, 1, 2).contiguous()
+        if gt is not None:
+            gt = gt.view(*shape).permute(0, 3, 1, 2).contiguous()
+        if self.test_cfg is not None and self.test_cfg.get("metrics", None):
+            assert gt is not None, "evaluation with metrics must have gt images."
+            results = dict(eval_result=self.evaluate(pred, gt))
+        else:
+            results = dict(lq=lq.cpu(), output=pred.cpu())
+            if gt is not None:
+                results["gt"] = gt.cpu()
+        if save_image:
+            import cv2
+            key = "gt_path" if "gt_path" in meta[0] else "lq_path"
+            folder_name = osp.splitext(osp.basename(meta[0][key]))[0]
+            if isinstance(iteration, numbers.Number):
+                save_path = osp.join(save_path, folder_name, f"{folder_name}-{iteration + 1:06d}.png")
+            elif iteration is None:
+                save_path = osp.join(save_path, f"{folder_name}.png")
+            else:
+                raise ValueError(f"iteration should be number or None, but got {type(iteration)}")
+            cv2.imwrite(save_path, tensor2img(pred))
+        return results
+
+    def init_weights(self, pretrained=None, strict=True):
+        self.generator.init_weights(pretrained, strict)
+
+    @staticmethod
+    def tile_origins(n, tile, overlap):
+        """Tile start offsets along one axis (ciaosr.py:227-229)."""
+        stride = tile - overlap
+        return list(range(0, n - tile, stride)) + [n - tile]
+
+    def clip_test(self, img_lq, model, denorm=False, tiles=None):
+        """Overlap-average tiled inference (ciaosr.py:218-258) -> [B, Ho*Wo, 3].
+
+        `tiles`: optional subset of tile indices to run (multi-GPU sharding); the
+        accumulators are then returned un-normalised as (acc, cnt).
+        """
+        sf = self.test_cfg.get("scale", None)
+        b, c, h, w = img_lq.size()
+        tile = min(self.test_cfg.get("tile", None), h, w)
+        overlap = self.test_cfg.get("tile_overlap", None)
+        origins = [(y0, x0) for y0 in self.tile_origins(h, tile, overlap)
+                   for x0 in self.tile_origins(w, tile, overlap)]
+        ho, wo = h * sf, w * sf
+        acc = torch.zeros(b, c, ho, wo, dtype=torch.float32, device=img_lq.device)
+        cnt = torch.zeros_like(acc)
+        th, tw = round(tile * sf), round(tile * sf)
+        hr_coord = make_coord((th, tw)).unsqueeze(0).expand(b, -1, 2).to(img_lq).contiguous()
+        cell = torch.ones_like(hr_coord)
+        cell[:, :, 0] *= 2 / th
+        cell[:, :, 1] *= 2 / tw
+        for ti, (y0, x0) in enumerate(origins):
+            if tiles is not None and ti not in tiles:
+                continue
+            patch = img_lq[..., y0:y0 + tile, x0:x0 + tile].contiguous()
+            out = model(patch, hr_coord, cell, test_mode=True)
+            native.tile_blend_accumulate(out, acc, cnt, y0 * sf, x0 * sf, th, tw)
+        if tiles is not None:
+            return acc, cnt
+        if denorm:
+            return native.tile_blend_finish(acc, cnt, self.gt_mean.to(acc), self.gt_std.to(acc), True)
+        return native.tile_blend_finish(acc, cnt)

@@ -1,0 +1,130 @@
+"""Mint golden vectors by RUNNING THE REFERENCE (build container only).
+
+    python -m oracle.make_golden            # rewrites tests/golden/*.npz
+
+The reference ships no tests and no golden vectors, so
+parity is pinned on outputs of the reference's own code, imported in place from
+/root/reference through oracle/ref_harness.py, on seeded synthetic weights and
+inputs (ciaosr_b200/synth.py; bit-stable numpy RandomState streams keyed on the
+state_dict key, so the weights themselves need not be stored).
+
+Each .npz holds the case's `meta` (JSON), its inputs and the reference's outputs.
+`/root/reference` does not travel to the GPU box; these files do.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ciaosr_b200 import synth  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def grid_coord_cell(b, h, w, s):
+    th, tw = round(h * s), round(w * s)
+    coord = rh.make_coord((th, tw)).unsqueeze(0).expand(b, -1, 2).contiguous()
+    cell = torch.ones_like(coord)
+    cell[:, :, 0] *= 2 / th
+    cell[:, :, 1] *= 2 / tw
+    return coord, cell
+
+
+def head_case(name, c, hidden, b, h, w, scales, eval_bsize, local_size=2, non_local=True,
+              seed=0, random_q=0):
+    g = rh.build_reference_generator("edsr", c, hidden, num_blocks=1, eval_bsize=eval_bsize,
+                                     local_size=local_size, non_local_attn=non_local)
+    synth.fill_module(g, seed)
+    feature = synth.synth_feature(b, c, h, w, seed)
+    x_lr = synth.synth_lr_image(b, h, w, seed)
+    g.gen_feature = lambda _x: [feature]
+    arrays = dict(feature=feature.numpy(), x_lr=x_lr.numpy())
+    with torch.no_grad():
+        if non_local:
+            arrays["nonlocal"] = g.cs_attn(feature).numpy()
+        runs = []
+        for s in scales:
+            coord, cell = grid_coord_cell(b, h, w, s)
+            runs.append((f"s{s}", coord, cell))
+        if random_q:
+            rs = np.random.RandomState(seed + 17)
+            coord = torch.from_numpy(rs.uniform(-1, 1, size=(b, random_q, 2)).astype(np.float32))
+            sc = rs.uniform(1.0, 4.0, size=(b, 1, 1)).astype(np.float32)
+            cell = torch.from_numpy(np.broadcast_to(
+                np.concatenate([2.0 / (h * sc), 2.0 / (w * sc)], axis=2), (b, random_q, 2)).copy())
+            runs.append(("rand", coord, cell))
+        for tag, coord, cell in runs:
+            arrays[f"coord_{tag}"] = coord.numpy()
+            arrays[f"cell_{tag}"] = cell.numpy()
+            arrays[f"pred_{tag}"] = g.query_rgb([feature], coord, cell).numpy()        # bare head, one chunk
+            arrays[f"out_{tag}"] = g(x_lr, coord, cell, test_mode=True).numpy()         # chunked + residual
+    meta = dict(kind="head", c=c, hidden=list(hidden), b=b, h=h, w=w, eval_bsize=eval_bsize,
+                local_size=local_size, non_local=non_local, seed=seed,
+                tags=[t for t, _, _ in runs])
+    save(name, meta, arrays)
+
+
+def csattn_case(name, c, b, h, w, seed=0):
+    ref = rh.import_reference()
+    m = ref.csnln.CrossScaleAttention(channel=c, scale=[2]).eval()
+    holder = torch.nn.Module()
+    holder.cs_attn = m
+    synth.fill_module(holder, seed)
+    feature = synth.synth_feature(b, c, h, w, seed)
+    with torch.no_grad():
+        out = m(feature)
+    save(name, dict(kind="csattn", c=c, b=b, h=h, w=w, seed=seed),
+         dict(feature=feature.numpy(), out=out.numpy()))
+
+
+def clip_case(name, c, hidden, h, w, scale, tile, overlap, seed=0):
+    ref = rh.import_reference()
+    g = rh.build_reference_generator("edsr", c, hidden, num_blocks=1, eval_bsize=500)
+    synth.fill_module(g, seed)
+    lq = synth.synth_lr_image(1, h, w, seed)
+    fake_self = types.SimpleNamespace(test_cfg=dict(scale=scale, tile=tile, tile_overlap=overlap))
+    with torch.no_grad():
+        out = ref.restorer.CiaoSR.clip_test(fake_self, lq, g)
+    save(name, dict(kind="clip", c=c, hidden=list(hidden), h=h, w=w, scale=scale, tile=tile,
+                    overlap=overlap, seed=seed, eval_bsize=500),
+         dict(lq=lq.numpy(), out=out.numpy()))
+
+
+def save(name, meta, arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                        **{k: np.ascontiguousarray(v, dtype=np.float32) for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB  {meta}")
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    # generic small shapes (SIMT engine): odd H (reflect pad), non-square, several chunks
+    head_case("head_small", 8, (32, 32), 2, 7, 6, [2, 3], eval_bsize=100, random_q=150)
+    head_case("head_frac", 8, (16,), 1, 6, 5, [2.5, 1.7], eval_bsize=None, seed=1)
+    head_case("head_ls1", 8, (16, 16), 1, 6, 6, [2], eval_bsize=50, local_size=1, seed=2)
+    head_case("head_ls3", 8, (16, 16), 1, 6, 6, [3], eval_bsize=None, local_size=3, seed=3)
+    head_case("head_nonl0", 16, (32, 32, 32), 2, 6, 8, [2, 4], eval_bsize=300, non_local=False, seed=4)
+    # the real head dimensions (tcgen05 engine): C=64, hidden 256x4
+    head_case("head_c64", 64, (256, 256, 256, 256), 2, 12, 10, [2, 4], eval_bsize=700, seed=5,
+              random_q=300)
+    head_case("head_c64_nonl0", 64, (256, 256, 256, 256), 1, 10, 12, [3], eval_bsize=None,
+              non_local=False, seed=6)
+    # cross-scale attention alone
+    csattn_case("csattn_c64", 64, 1, 24, 20, seed=7)
+    csattn_case("csattn_odd", 16, 2, 9, 11, seed=8)
+    # tiled inference through the restorer
+    clip_case("clip_small", 16, (32, 32), 40, 36, 2, 24, 8, seed=9)
+
+
+if __name__ == "__main__":
+    main()
