@@ -38,6 +38,13 @@ EVAL_BSIZE = 30000
 RGB_MEAN = (0.4488, 0.4371, 0.4040)
 
 
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def model_cfg(engine="auto"):
     from ciaosr_b200.generators import LocalImplicitSRRDN
     from ciaosr_b200.restorers import CiaoSR
@@ -162,7 +169,7 @@ def cpu_reference_sample(steps, warmup, threads):
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = int(os.environ.get("CIAOSR_CPU_THREADS", os.cpu_count() or 1))
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     val, ms = cpu_reference_sample(steps, warmup, threads)
     sample = f"1 of the {B} LR 48x48 crops -> x4 (36 864 px) per step, {steps} steps"
@@ -259,11 +266,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps, launches, stages
 
+    log("model + inputs ready")
     for _ in range(args.warmup):
         step_device()
+    torch.cuda.synchronize()
+    log("warm-up done")
     with ClockSampler(local) as clk:
         ms_step, launches, stages = timed(step_device, args.steps, profile=True)
     clocks = clk.summary()
+    log(f"timed region done: {ms_step:.1f} ms/step")
     # head alone (feature resident): what the roofline explains
     with torch.no_grad():
         feat = gen.gen_feature(lq_d)
@@ -272,6 +283,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    log(f"head {ms_head:.1f} ms, encoder {ms_enc:.1f} ms, e2e {ms_e2e:.1f} ms")
 
     if rank == 0:
         from oracle.ciaosr_oracle import cross_scale_flops, head_flops_per_query
@@ -309,8 +321,9 @@ def main():
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = int(os.environ.get("CIAOSR_CPU_THREADS", os.cpu_count() or 1))
             val, ms = cpu_reference_sample(2, 1, threads)
+            log(f"cpu baseline done: {ms:.0f} ms per sample on {threads} threads")
             line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
                                     "sample": "1 of the 16 crops (36 864 px), 2 timed runs, %.0f ms each" % ms}
         print(json.dumps(line), flush=True)

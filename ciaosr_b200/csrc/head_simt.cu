@@ -37,7 +37,7 @@ struct PairProdA {     // A[pix*9 + d, kp] = U[pix, kp] * U[pix + d, kp]   (kp <
 };
 
 int run_lr_precompute(const PlanLayout& L, const float* plan, const HeadArgs& a, float* Pk,
-                      float* Pv, float* G, cudaStream_t st) {
+                      float* Pv, float* G, int ldg, cudaStream_t st) {
   const int npix = a.B * a.H * a.W;
   const int H1k = L.k.dims[1], H1v = L.v.dims[1], Hlk = L.k.dims[L.k.n_layers - 1];
   int rc;
@@ -47,7 +47,7 @@ int run_lr_precompute(const PlanLayout& L, const float* plan, const HeadArgs& a,
   if ((rc = gemm_simt(npix, H1v, L.Dv, ua, RowMajorB{plan + L.v.wt[0], H1v},
                       EpiBiasAct{Pv, H1v, nullptr, 0}, st))) return rc;
   if ((rc = gemm_simt(npix * 9, Hlk + 1, L.Dk, PairProdA{a.featT, a.H, a.W, L.C},
-                      RowMajorB{plan + L.k.fin, Hlk + 1}, EpiBiasAct{G, Hlk + 1, nullptr, 0}, st)))
+                      RowMajorB{plan + L.k.fin, Hlk + 1}, EpiBiasAct{G, ldg, nullptr, 0}, st)))
     return rc;
   return CIAOSR_OK;
 }
@@ -99,7 +99,7 @@ pair_layer1_kernel(PairConsts pc, const float* __restrict__ coord, const float* 
 
 // one warp per row: logit = h . G[gidx, :Hl] + G[gidx, Hl]
 __global__ void pair_logits_kernel(const float* __restrict__ hk, const float* __restrict__ G,
-                                   const int* __restrict__ pair_g, int nrows, int Hl,
+                                   const int* __restrict__ pair_g, int nrows, int Hl, int ldg,
                                    float* __restrict__ logits) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= nrows) return;
@@ -107,7 +107,7 @@ __global__ void pair_logits_kernel(const float* __restrict__ hk, const float* __
   const int g = pair_g[r];
   float s = 0.0f;
   if (g >= 0) {
-    const float* gr = G + (long long)g * (Hl + 1);
+    const float* gr = G + (long long)g * ldg;
     const float* hr = hk + (long long)r * Hl;
     for (int h = lane; h < Hl; h += 32) s = fmaf(hr[h], gr[h], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -161,6 +161,8 @@ struct EpiRgbOut {     // out[g, n] = acc + b[n] (+ bilinear residual of the LR 
 // ---- host orchestration -----------------------------------------------------------
 static int simt_chunk(long long total) { return (int)(total < 32768 ? total : 32768); }
 
+static int simt_ldg(const PlanLayout& L) { return (L.k.dims[L.k.n_layers - 1] + 1 + 3) / 4 * 4; }
+
 static int max_hidden(const MlpPlan& p) {
   int m = 0;
   for (int l = 1; l < p.n_layers; ++l) m = m > p.dims[l] ? m : p.dims[l];
@@ -182,7 +184,7 @@ static SimtBufs simt_carve(Arena& a, const PlanLayout& L, int B, int H, int W, i
   hm = hm > max_hidden(L.q) ? hm : max_hidden(L.q);
   s.Pk = a.take<float>(npix * L.k.dims[1]);
   s.Pv = a.take<float>(npix * L.v.dims[1]);
-  s.G = a.take<float>(npix * 9 * (L.k.dims[L.k.n_layers - 1] + 1));
+  s.G = a.take<float>(npix * 9 * simt_ldg(L));
   s.bufA = a.take<float>(rows * hm);
   s.bufB = a.take<float>(rows * hm);
   s.bufC = a.take<float>(rows * hm);
@@ -209,7 +211,7 @@ int run_head_simt(const PlanLayout& L, const float* plan, const HeadArgs& a, voi
   int rc;
   {
     StageScope sc(2, st);
-    if ((rc = run_lr_precompute(L, plan, a, s.Pk, s.Pv, s.G, st))) return rc;
+    if ((rc = run_lr_precompute(L, plan, a, s.Pk, s.Pv, s.G, simt_ldg(L), st))) return rc;
   }
 
   const long long total = (long long)a.B * a.Q;
@@ -236,7 +238,7 @@ int run_head_simt(const PlanLayout& L, const float* plan, const HeadArgs& a, voi
                           EpiBiasAct{other, L.k.dims[l + 1], plan + L.k.bias[l], 1}, st))) return rc;
       float* t = cur; cur = other; other = t;
     }
-    CIAOSR_LAUNCH(pair_logits_kernel, cdiv(rows, 8), 256, 0, st, cur, s.G, s.pair_g, rows, Hlk, s.logits);
+    CIAOSR_LAUNCH(pair_logits_kernel, cdiv(rows, 8), 256, 0, st, cur, s.G, s.pair_g, rows, Hlk, simt_ldg(L), s.logits);
     // value chain: hidden layers in bufB <-> bufA, last layer -> wv
     cur = hv;
     other = s.bufA;

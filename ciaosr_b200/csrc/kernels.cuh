@@ -30,8 +30,9 @@ size_t head_simt_workspace(const PlanLayout& L, int B, int H, int W, int Q);
 int run_head_simt(const PlanLayout& L, const float* plan, const HeadArgs& a, void* ws,
                   size_t ws_bytes, cudaStream_t st);
 // LR-resolution precompute shared by both engines: Pk, Pv (layer-1 hoist, no bias) and G (key fold)
+// G is [B*H*W*9, ldg] with ldg >= H_last + 1 (column H_last holds the folded bias term)
 int run_lr_precompute(const PlanLayout& L, const float* plan, const HeadArgs& a, float* Pk,
-                      float* Pv, float* G, cudaStream_t st);
+                      float* Pv, float* G, int ldg, cudaStream_t st);
 
 // head_tc.cu
 size_t head_tc_workspace(const PlanLayout& L, int B, int H, int W, int Q);
