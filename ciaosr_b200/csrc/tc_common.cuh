@@ -49,8 +49,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
       printf("ciaosr tcgen05: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
              blockIdx.x, threadIdx.x, parity);
       __trap();
