@@ -27,7 +27,7 @@ EXPORTS = (
     "ciaosr_last_error", "ciaosr_abi_version", "ciaosr_launch_count",
     "ciaosr_engine_supported", "ciaosr_profile_enable", "ciaosr_profile_read",
     "ciaosr_plan_bytes", "ciaosr_plan_init", "ciaosr_workspace_bytes",
-    "ciaosr_cross_scale_attn_forward", "ciaosr_query_rgb_forward",
+    "ciaosr_cross_scale_attn_workspace_bytes", "ciaosr_cross_scale_attn_forward", "ciaosr_query_rgb_forward",
     "ciaosr_tile_blend_accumulate", "ciaosr_tile_blend_finish",
 )
 
@@ -95,8 +95,10 @@ def load():
     lib.ciaosr_plan_init.argtypes = [POINTER(HeadDesc), c_void_p, c_size_t, c_void_p]
     lib.ciaosr_workspace_bytes.argtypes = [POINTER(HeadDesc), c_int, c_int, c_int, c_int, c_int,
                                            POINTER(c_size_t)]
+    lib.ciaosr_cross_scale_attn_workspace_bytes.argtypes = [POINTER(HeadDesc), c_int, c_int, c_int, c_int,
+                                                            POINTER(c_size_t)]
     lib.ciaosr_cross_scale_attn_forward.argtypes = [
-        POINTER(HeadDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+        POINTER(HeadDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
         c_void_p]
     lib.ciaosr_query_rgb_forward.argtypes = [
         POINTER(HeadDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

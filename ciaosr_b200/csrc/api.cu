@@ -82,7 +82,8 @@ static CallLayout carve_call(const PlanLayout& L, int engine, int B, int H, int 
   c.nlT = a.take<float>((size_t)B * H * W * (L.Cn > 0 ? L.Cn : 1));
   size_t inner = engine_ws(L, engine, B, H, W, Q);
   if (L.non_local) {
-    const size_t csa = cs_attn_workspace(L, H, W);
+    const size_t csa = (engine == CIAOSR_ENGINE_TCGEN05 && cs_attn_tc_ok(L)) ? cs_attn_tc_workspace(L, B, H, W)
+                                                                              : cs_attn_workspace(L, H, W);
     inner = inner > csa ? inner : csa;
   }
   c.rest = a.take<char>(inner);
@@ -171,24 +172,52 @@ int ciaosr_workspace_bytes(const ciaosr_head_desc* desc, int B, int H, int W, in
   return CIAOSR_OK;
 }
 
+static int cs_engine(const PlanLayout& L, int engine, bool* use_tc) {
+  CIAOSR_REQUIRE(L.non_local, CIAOSR_E_INVALID, "desc.non_local_attn is 0: no cross-scale attention");
+  CIAOSR_REQUIRE(engine >= CIAOSR_ENGINE_AUTO && engine <= CIAOSR_ENGINE_TCGEN05, CIAOSR_E_INVALID,
+                 "unknown engine %d", engine);
+  CIAOSR_REQUIRE(engine != CIAOSR_ENGINE_TCGEN05 || cs_attn_tc_ok(L), CIAOSR_E_INVALID,
+                 "tcgen05 cross-scale attention needs C %% 8 == 0");
+  *use_tc = engine != CIAOSR_ENGINE_SIMT && cs_attn_tc_ok(L);
+  return CIAOSR_OK;
+}
+
+int ciaosr_cross_scale_attn_workspace_bytes(const ciaosr_head_desc* desc, int B, int H, int W, int engine,
+                                            size_t* bytes) {
+  CIAOSR_REQUIRE(bytes != nullptr, CIAOSR_E_INVALID, "bytes is NULL");
+  CIAOSR_REQUIRE(B > 0 && H > 0 && W > 0, CIAOSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, H, W);
+  PlanLayout L;
+  int rc = plan_layout(desc, &L);
+  if (rc) return rc;
+  bool use_tc;
+  if ((rc = cs_engine(L, engine, &use_tc))) return rc;
+  Arena a(nullptr, 0);
+  a.take<float>((size_t)B * H * W * L.C);
+  a.take<char>(use_tc ? cs_attn_tc_workspace(L, B, H, W) : cs_attn_workspace(L, H, W));
+  *bytes = a.used();
+  return CIAOSR_OK;
+}
+
 int ciaosr_cross_scale_attn_forward(const ciaosr_head_desc* desc, const void* plan,
-                                    const float* feature, int B, int H, int W, float* out,
+                                    const float* feature, int B, int H, int W, int engine, float* out,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   PlanLayout L;
   if ((rc = plan_layout(desc, &L))) return rc;
-  CIAOSR_REQUIRE(L.non_local, CIAOSR_E_INVALID, "desc.non_local_attn is 0: no cross-scale attention");
   CIAOSR_REQUIRE(plan && feature && out, CIAOSR_E_INVALID, "NULL pointer argument");
   CIAOSR_REQUIRE(B > 0 && H > 0 && W > 0, CIAOSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, H, W);
+  bool use_tc;
+  if ((rc = cs_engine(L, engine, &use_tc))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Arena a(workspace, workspace_bytes);
   float* featT = a.take<float>((size_t)B * H * W * L.C);
-  const size_t inner = cs_attn_workspace(L, H, W);
+  const size_t inner = use_tc ? cs_attn_tc_workspace(L, B, H, W) : cs_attn_workspace(L, H, W);
   void* rest = a.take<char>(inner);
   CIAOSR_REQUIRE(workspace && a.ok, CIAOSR_E_WORKSPACE, "workspace too small: need %zu, have %zu",
                  a.used(), workspace_bytes);
   if ((rc = transpose_batched(feature, featT, B, L.C, H * W, st))) return rc;
+  if (use_tc) return run_cs_attn_tc(L, (const float*)plan, featT, B, H, W, nullptr, 0, out, rest, inner, st);
   return run_cs_attn(L, (const float*)plan, featT, B, H, W, nullptr, 0, out, rest, inner, st);
 }
 
@@ -223,8 +252,11 @@ int ciaosr_query_rgb_forward(const ciaosr_head_desc* desc, const void* plan, con
   }
   if (L.non_local && !nonlocal) {
     StageScope sc(1, st);
-    if ((rc = run_cs_attn(L, (const float*)plan, c.featT, B, H, W, c.nlT, L.Cn, nullptr, c.rest,
-                          c.rest_bytes, st))) return rc;
+    if (eng == CIAOSR_ENGINE_TCGEN05 && cs_attn_tc_ok(L)) {
+      if ((rc = run_cs_attn_tc(L, (const float*)plan, c.featT, B, H, W, c.nlT, L.Cn, nullptr, c.rest,
+                               c.rest_bytes, st))) return rc;
+    } else if ((rc = run_cs_attn(L, (const float*)plan, c.featT, B, H, W, c.nlT, L.Cn, nullptr, c.rest,
+                                 c.rest_bytes, st))) return rc;
   }
   HeadArgs a;
   a.B = B; a.H = H; a.W = W; a.Q = q; a.eval_bsize = eval_bsize;

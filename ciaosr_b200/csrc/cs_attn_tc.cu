@@ -1,0 +1,343 @@
+// Cross-scale non-local attention on the tensor cores (arch_csnln.py:430-532).
+//
+// Same attention form as cs_attn.cu (see its header), with the three large contractions on
+// tcgen05 through the generic functor GEMM (gemm_tc.cuh, bf16x3 = fp32-grade):
+//   S = 10 * Q K^T        A = 3x3 patches of Mi (implicit), B = normalised 3x3 patches of R (packed per image)
+//   O = P V               A = softmax rows,                 B = V^T: 6x6 stride-2 patches of E (packed per image)
+//   out = down(canvas)/6  A = 3x3 stride-2 patches of the folded canvas, B = down-conv weights
+// The 1x1 embeddings, the row softmax and the fold stay on CUDA cores (they are bandwidth-trivial),
+// batched over all images of the call.
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace ciaosr {
+
+// ---- batched CUDA-core pieces --------------------------------------------------------------------
+struct PadFeatBatchA {      // A[(img, y, x) in padded coords, ci], reflect pad bottom/right
+  const float* f; int H, W, Hp, Wp, C;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    const int img = m / (Hp * Wp), r = m % (Hp * Wp);
+    int y = r / Wp, x = r % Wp;
+    if (y >= H) y = 2 * (H - 1) - y;
+    if (x >= W) x = 2 * (W - 1) - x;
+    return f[(((long long)img * H + y) * W + x) * C + k];
+  }
+};
+struct PoolFeatBatchA {     // 2x2 average of the padded image
+  const float* f; int H, W, Hl, Wl, C;
+  __device__ __forceinline__ float at(int img, int y, int x, int k) const {
+    if (y >= H) y = 2 * (H - 1) - y;
+    if (x >= W) x = 2 * (W - 1) - x;
+    return f[(((long long)img * H + y) * W + x) * C + k];
+  }
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    const int img = m / (Hl * Wl), r = m % (Hl * Wl);
+    const int y = 2 * (r / Wl), x = 2 * (r % Wl);
+    const float r0 = at(img, y, x, k) * 0.5f + at(img, y + 1, x, k) * 0.5f;
+    const float r1 = at(img, y, x + 1, k) * 0.5f + at(img, y + 1, x + 1, k) * 0.5f;
+    return r0 * 0.5f + r1 * 0.5f;
+  }
+};
+struct EpiPrelu {
+  float* c; int ldc; const float* bias; const float* slope;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    const float v = acc + bias[n];
+    c[(long long)m * ldc + n] = v >= 0.0f ? v : v * slope[0];
+  }
+};
+
+__global__ void csa_knorm_batch_kernel(const float* __restrict__ r, float* __restrict__ nrm, int Hl, int Wl,
+                                       int Ch, const float* __restrict__ scalars) {
+  const int gl = blockIdx.x, img = gl / (Hl * Wl), l = gl % (Hl * Wl);
+  const float* ri = r + (long long)img * Hl * Wl * Ch;
+  float ss = 0.0f;
+  for (int i = threadIdx.x; i < 9 * Ch; i += blockDim.x) {
+    const int t = i / Ch, c = i % Ch;
+    const int y = l / Wl + t / 3 - 1, x = l % Wl + t % 3 - 1;
+    if (y >= 0 && y < Hl && x >= 0 && x < Wl) {
+      const float v = ri[((long long)y * Wl + x) * Ch + c];
+      ss = fmaf(v, v, ss);
+    }
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ss = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (threadIdx.x == 0) nrm[gl] = fmaxf(sqrtf(ss), scalars[3]);
+  }
+}
+
+// one warp per row; the row (L <= a few thousand) is cached in registers when it fits
+__global__ void softmax_rows_ld_kernel(float* __restrict__ s, long long rows, int L, int ld) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* p = s + row * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < L; i += 32) mx = fmaxf(mx, p[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.0f;
+  for (int i = lane; i < L; i += 32) {
+    const float e = expf(p[i] - mx);
+    p[i] = e;
+    sum += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int i = lane; i < L; i += 32) p[i] = __fdiv_rn(p[i], sum);
+}
+
+__global__ void csa_fold_batch_kernel(const float* __restrict__ o, float* __restrict__ cv, int Hp, int Wp,
+                                      int C, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long p = i / C;
+  const int W2 = 2 * Wp, H2 = 2 * Hp;
+  const int X = (int)(p % W2), Y = (int)((p / W2) % H2);
+  const long long img = p / ((long long)W2 * H2);
+  const float* oi = o + img * Hp * Wp * 36LL * C;
+  float acc = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int y = Y / 2 + 1 - a;
+    if (y < 0 || y >= Hp) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int x = X / 2 + 1 - b;
+      if (x < 0 || x >= Wp) continue;
+      const int ij = (Y % 2 + 2 * a) * 6 + (X % 2 + 2 * b);
+      acc += oi[((long long)y * Wp + x) * (36LL * C) + (long long)ij * C + c];
+    }
+  }
+  cv[i] = acc;
+}
+
+// ---- operand sources for the per-image blobs ----------------------------------------------------
+struct KhatSrc {            // B[n = l, k = t*Ch + c] = R_pad[l + tap t, c] / max(|patch l|, eps)
+  const float* r; const float* nrm; int Hl, Wl, Ch, img0;
+  __device__ __forceinline__ float operator()(int image, int n, int k) const {
+    const int img = img0 + image, t = k / Ch, c = k % Ch;
+    const int y = n / Wl + t / 3 - 1, x = n % Wl + t % 3 - 1;
+    if (y < 0 || y >= Hl || x < 0 || x >= Wl) return 0.0f;
+    return __fdiv_rn(r[(((long long)img * Hl + y) * Wl + x) * Ch + c], nrm[(long long)img * Hl * Wl + n]);
+  }
+};
+struct VtSrc {              // B[n = (i*6+j)*C + c, k = l] = E_pad[c, 2ly-2+i, 2lx-2+j]
+  const float* e; int Hp, Wp, Wl, C, img0;
+  __device__ __forceinline__ float operator()(int image, int n, int k) const {
+    const int img = img0 + image, ij = n / C, c = n % C;
+    const int y = 2 * (k / Wl) - 2 + ij / 6, x = 2 * (k % Wl) - 2 + ij % 6;
+    if (y < 0 || y >= Hp || x < 0 || x >= Wp) return 0.0f;
+    return e[(((long long)img * Hp + y) * Wp + x) * C + c];
+  }
+};
+struct DownSrc {            // B[n = co, k = (u*3+v)*C + ci] = down_wt[k, co]
+  const float* w; int C;
+  __device__ __forceinline__ float operator()(int, int n, int k) const { return w[(long long)k * C + n]; }
+};
+
+// ---- A generators / epilogues ----------------------------------------------------------------------
+struct QPatchGen {          // rows = (img, y, x) of the group; k = t*Ch + c, Ch % 4 == 0
+  const float* mi; int Hp, Wp, Ch, K; long long pix0;
+  struct Row { int y, x; long long pix; };
+  __device__ __forceinline__ Row row(long long m) const {
+    const long long p = pix0 + m;
+    const int r = (int)(p % ((long long)Hp * Wp));
+    return Row{r / Wp, r % Wp, p};
+  }
+  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const int t = k / Ch, c = k - t * Ch;
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        if (r.y + dy >= 0 && r.y + dy < Hp && r.x + dx >= 0 && r.x + dx < Wp)
+          q = __ldg(reinterpret_cast<const float4*>(mi + (r.pix + dy * Wp + dx) * Ch + c));
+      }
+      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+  }
+};
+struct ScoreEpi {           // S[m, n] = scale * acc, n < L
+  float* s; int L, ld; float scale;
+  __device__ __forceinline__ void store(const QPatchGen::Row&, long long m, int n0, const float (&v)[32]) const {
+    float* dst = s + m * ld + n0;
+    if (n0 + 32 <= L) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] =
+            make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale, v[4 * j + 3] * scale);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < L) dst[i] = v[i] * scale;
+    }
+  }
+};
+struct ProbGen {            // A = P rows (fp32, ld % 4 == 0), K = L
+  const float* p; int K, ld;
+  struct Row { const float* r; };
+  __device__ __forceinline__ Row row(long long m) const { return Row{p + m * ld}; }
+  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k + 4 <= K) q = __ldg(reinterpret_cast<const float4*>(r.r + k));
+      else if (k < K) {
+        q.x = r.r[k];
+        if (k + 1 < K) q.y = r.r[k + 1];
+        if (k + 2 < K) q.z = r.r[k + 2];
+      }
+      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+  }
+};
+struct OutEpi {             // O[m, n] = acc, n < N (N % 4 == 0)
+  float* o; int N;
+  __device__ __forceinline__ void store(const ProbGen::Row&, long long m, int n0, const float (&v)[32]) const {
+    float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + 4 * j < N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+};
+struct DownGen {            // rows = cropped output pixels (img, y, x); k = (u*3+v)*C + ci
+  const float* cv; int H, W, H2, W2, C, K; long long img0;
+  struct Row { int y, x, hw; long long img; };
+  __device__ __forceinline__ Row row(long long m) const {
+    const int hw = (int)(m % ((long long)H * W));
+    return Row{hw / W, hw % W, hw, m / ((long long)H * W)};
+  }
+  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const int uv = k / C, ci = k - uv * C;
+        const int Y = 2 * r.y - 1 + uv / 3, X = 2 * r.x - 1 + uv % 3;
+        if (Y >= 0 && Y < H2 && X >= 0 && X < W2)
+          q = __ldg(reinterpret_cast<const float4*>(cv + (((r.img * H2) + Y) * W2 + X) * C + ci));
+      }
+      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+  }
+};
+struct DownEpi {            // (acc + b) / 6 -> NHWC slice and / or NCHW
+  float* o_nhwc; int ldo; float* o_nchw; int HW, C; const float* bias; long long img0;
+  __device__ __forceinline__ void store(const DownGen::Row& r, long long m, int n0, const float (&v)[32]) const {
+    const long long gm = img0 * HW + m;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int n = n0 + i;
+      if (n < C) {
+        const float val = __fdiv_rn(v[i] + bias[n], 6.0f);
+        if (o_nhwc) o_nhwc[gm * ldo + n] = val;
+        if (o_nchw) o_nchw[((img0 + r.img) * C + n) * HW + r.hw] = val;
+      }
+    }
+  }
+};
+
+// ---- host orchestration ------------------------------------------------------------------------------
+struct CsaTcSizes {
+  int Hp, Wp, Hl, Wl, L, ldS, HWp, group;      // group = images processed together
+  int kq_slabs, kq_units, vt_slabs, vt_units, dn_slabs, dn_units;
+};
+static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
+  CsaTcSizes s;
+  s.Hp = H + (H & 1); s.Wp = W + (W & 1);
+  s.Hl = s.Hp / 2; s.Wl = s.Wp / 2; s.L = s.Hl * s.Wl; s.ldS = (s.L + 3) / 4 * 4;
+  s.HWp = s.Hp * s.Wp;
+  s.kq_slabs = (9 * (C / 2) + KSLAB - 1) / KSLAB; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
+  s.vt_slabs = (s.L + KSLAB - 1) / KSLAB; s.vt_units = (36 * C + UNIT_N - 1) / UNIT_N;
+  s.dn_slabs = (9 * C + KSLAB - 1) / KSLAB; s.dn_units = (C + UNIT_N - 1) / UNIT_N;
+  // images per pass: tiles must not straddle images, and the score tensor stays <= 1 GiB
+  long long g = (256LL << 20) / ((long long)s.HWp * s.ldS);
+  if (g < 1) g = 1;
+  if (g > B) g = B;
+  if (s.HWp % ROWS != 0) g = 1;
+  s.group = (int)g;
+  return s;
+}
+
+bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 8 == 0; }
+
+struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; uint8_t *kblob, *vblob, *dblob; };
+static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s, int B) {
+  CsaTcBufs b;
+  const int C = L.C, Ch = C / 2, g = s.group;
+  b.E = a.take<float>((size_t)B * s.HWp * C);
+  b.Mi = a.take<float>((size_t)B * s.HWp * Ch);
+  b.R = a.take<float>((size_t)B * s.L * Ch);
+  b.nrm = a.take<float>((size_t)B * s.L);
+  b.S = a.take<float>((size_t)g * s.HWp * s.ldS);
+  b.O = a.take<float>((size_t)g * s.HWp * 36 * C);
+  b.cv = a.take<float>((size_t)g * 4 * s.HWp * C);
+  b.kblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.kq_slabs, s.kq_units));
+  b.vblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.vt_slabs, s.vt_units));
+  b.dblob = a.take<uint8_t>(tc_operand_blob_bytes(s.dn_slabs, s.dn_units));
+  return b;
+}
+
+size_t cs_attn_tc_workspace(const PlanLayout& L, int B, int H, int W) {
+  Arena a(nullptr, 0);
+  csa_tc_carve(a, L, csa_tc_sizes(B, H, W, L.C), B);
+  return a.used();
+}
+
+int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, int B, int H, int W,
+                   float* out_nhwc, int ldo, float* out_nchw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CIAOSR_REQUIRE(H >= 2 && W >= 2, CIAOSR_E_INVALID,
+                 "cross-scale attention needs H, W >= 2 (reflect padding), got %dx%d", H, W);
+  const CsaTcSizes s = csa_tc_sizes(B, H, W, L.C);
+  const int C = L.C, Ch = C / 2;
+  Arena a(ws, ws_bytes);
+  CsaTcBufs b = csa_tc_carve(a, L, s, B);
+  CIAOSR_REQUIRE(a.ok, CIAOSR_E_WORKSPACE, "cross-scale attention workspace too small: need %zu, have %zu",
+                 a.used(), ws_bytes);
+  const float* scal = plan + L.scalars;
+  int rc;
+  // embeddings for every image of the call
+  PadFeatBatchA pa{featT, H, W, s.Hp, s.Wp, C};
+  if ((rc = gemm_simt(B * s.HWp, C, C, pa, RowMajorB{plan + L.as_wt, C},
+                      EpiPrelu{b.E, C, plan + L.as_b, scal + 2}, st))) return rc;
+  if ((rc = gemm_simt(B * s.HWp, Ch, C, pa, RowMajorB{plan + L.m1_wt, Ch},
+                      EpiPrelu{b.Mi, Ch, plan + L.m1_b, scal + 0}, st))) return rc;
+  if ((rc = gemm_simt(B * s.L, Ch, C, PoolFeatBatchA{featT, H, W, s.Hl, s.Wl, C}, RowMajorB{plan + L.m2_wt, Ch},
+                      EpiPrelu{b.R, Ch, plan + L.m2_b, scal + 1}, st))) return rc;
+  CIAOSR_LAUNCH(csa_knorm_batch_kernel, B * s.L, 128, 0, st, b.R, b.nrm, s.Hl, s.Wl, Ch, scal);
+  if ((rc = tc_pack_operand(b.dblob, 1, C, 9 * C, 0, DownSrc{plan + L.down_wt, C}, st))) return rc;
+
+  const size_t kstride = tc_operand_blob_bytes(s.kq_slabs, s.kq_units);
+  const size_t vstride = tc_operand_blob_bytes(s.vt_slabs, s.vt_units);
+  for (int i0 = 0; i0 < B; i0 += s.group) {
+    const int g = min(s.group, B - i0);
+    const long long rows = (long long)g * s.HWp;
+    if ((rc = tc_pack_operand(b.kblob, g, s.L, 9 * Ch, kstride, KhatSrc{b.R, b.nrm, s.Hl, s.Wl, Ch, i0}, st)))
+      return rc;
+    if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob,
+                      QPatchGen{b.Mi, s.Hp, s.Wp, Ch, 9 * Ch, (long long)i0 * s.HWp},
+                      ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st))) return rc;
+    CIAOSR_LAUNCH(softmax_rows_ld_kernel, cdiv(rows, 8), 256, 0, st, b.S, rows, s.L, s.ldS);
+    if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
+      return rc;
+    if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride}, b.vblob,
+                      ProbGen{b.S, s.L, s.ldS}, OutEpi{b.O, 36 * C}, st))) return rc;
+    const long long ctot = (long long)g * 4 * s.HWp * C;
+    CIAOSR_LAUNCH(csa_fold_batch_kernel, cdiv(ctot, 256), 256, 0, st, b.O, b.cv, s.Hp, s.Wp, C, ctot);
+    if ((rc = tc_gemm(GemmShape{(long long)g * H * W, s.dn_slabs, s.dn_units, (long long)g * H * W, 0}, b.dblob,
+                      DownGen{b.cv, H, W, 2 * s.Hp, 2 * s.Wp, C, 9 * C, 0},
+                      DownEpi{out_nhwc, ldo, out_nchw, H * W, C, plan + L.down_b, i0}, st))) return rc;
+  }
+  return CIAOSR_OK;
+}
+
+}  // namespace ciaosr

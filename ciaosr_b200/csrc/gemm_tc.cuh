@@ -1,0 +1,153 @@
+// Generic tcgen05 GEMM with functor-generated A rows:  C[m, n] = sum_k A(m, k) * B[n, k]
+//
+//   A  is produced on the fly, one thread per row (implicit im2col / patch extraction / pair
+//      products), split into bf16 hi/lo and written into the SW128 operand slabs;
+//   B  is a pre-swizzled unit blob ([128 N x 64 K] hi+lo, 32 KB each) in global memory: static
+//      weights packed at plan time, or per-image operands packed by a small kernel just before;
+//   C  leaves through an epilogue functor that sees 32 consecutive columns of one row.
+//
+// A job = (128-row tile, N-chunk of <= 256 columns); A is regenerated per job (K may exceed the
+// 256 columns that fit the four operand slots, so slabs stream through them under A_FREE).
+// Same pipeline, barriers and bf16x3 arithmetic as head_tc.cu (tc_pipeline.cuh).
+#pragma once
+#include "tc_pipeline.cuh"
+
+namespace ciaosr {
+
+struct GemmShape {
+  long long M;             // rows
+  int kslabs;              // ceil(K / 64)
+  int nunits;              // ceil(N / 128): weight units per K-slab over the whole N
+  long long rows_per_image;    // B operand switches every this many rows (M if shared)
+  size_t blob_image_stride;    // bytes between per-image blobs (0 if shared)
+};
+
+// AGen:  struct Row;  __device__ Row row(long long m) const;
+//        __device__ void fill(Row&, long long m, int k0, float (&v)[32]) const;     (k0 % 32 == 0)
+// Epi:   __device__ void store(const typename AGen::Row&, long long m, int n0, const float (&v)[32]) const;
+template <class AGen, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcShared s = tc_carve(smem);
+  const uint32_t tmem_base = tc_prologue(s, smem);
+  const int warp = threadIdx.x >> 5;
+  const int m_tiles = (int)((g.M + ROWS - 1) / ROWS);
+  const int n_chunks = (g.nunits + 1) / 2;
+  const long long n_jobs = (long long)m_tiles * n_chunks;
+
+  if (warp == 0) {
+    ProdState ps{0, 0};
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
+      const int units = min(2, g.nunits - 2 * nc);
+      const long long image = ((long long)mt * ROWS) / g.rows_per_image;
+      // blob order: for chunk: for slab: for unit
+      const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES;
+      produce_units(s, ps, src, g.kslabs * units);
+    }
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0, 0};
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int nc = (int)(job % n_chunks);
+      mma_job(s, tmem_base, m, g.kslabs, min(2, g.nunits - 2 * nc), true);
+    }
+  } else if (warp >= 4) {
+    const int row = threadIdx.x - EPI_T0;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu};
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
+      const int units = min(2, g.nunits - 2 * nc);
+      const long long m = (long long)mt * ROWS + row;
+      const bool valid = m < g.M;
+      typename AGen::Row rs = agen.row(valid ? m : 0);
+#pragma unroll 1
+      for (int sl = 0; sl < g.kslabs; ++sl) {
+        const int slot = sl & 3;
+        slab_begin(s, e, slot, true);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+          a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+        }
+        slab_done(s, slot);
+      }
+      const uint32_t d = epi_wait_d(s, e);
+#pragma unroll 1
+      for (int cc = 0; cc < units * 4; ++cc) {
+        float v[32];
+        tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
+        if (valid) epi.store(rs, m, nc * 256 + cc * 32, v);
+      }
+      epi_release_d(s, e);
+    }
+  }
+  tc_epilogue_dealloc(tmem_base);
+}
+
+inline int tc_grid_size(long long n_jobs) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int)(n_jobs < sms ? n_jobs : sms);
+}
+
+template <class AGen, class Epi>
+static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, const Epi& epi, cudaStream_t st) {
+  if (g.M <= 0) return CIAOSR_OK;
+  static bool attr_set = false;      // one per template instantiation
+  if (!attr_set) {
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<AGen, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SM_TOTAL));
+    attr_set = true;
+  }
+  const long long n_jobs = ((g.M + ROWS - 1) / ROWS) * ((g.nunits + 1) / 2);
+  CIAOSR_LAUNCH((tc_gemm_kernel<AGen, Epi>), tc_grid_size(n_jobs), TC_THREADS, SM_TOTAL, st, g, blob, agen, epi);
+  return CIAOSR_OK;
+}
+
+// Pack a [N, K] operand into the unit blob: element (n, k) = src(n, k) (0 outside N x K).
+// Blob order: chunk (256 N) -> slab (64 K) -> unit (128 N); units past nunits are absent.
+template <class Src>
+__global__ void tc_pack_operand_kernel(uint8_t* __restrict__ dst, int N, int K, int kslabs, int nunits,
+                                       size_t image_stride, const Src src) {
+  const long long per_image = (long long)kslabs * nunits * UNIT_N * KSLAB;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= per_image) return;
+  const int image = blockIdx.y;
+  const int k_in = (int)(i % KSLAB);
+  const int n_in = (int)((i / KSLAB) % UNIT_N);
+  const int rest = (int)(i / (KSLAB * UNIT_N));      // enumerates (unit_global, slab) pairs
+  const int ug = rest % nunits, sl = rest / nunits;
+  const int n = ug * UNIT_N + n_in, k = sl * KSLAB + k_in;
+  const float w = (n < N && k < K) ? src(image, n, k) : 0.0f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const int nc = ug / 2, u = ug % 2;
+  const int units = min(2, nunits - 2 * nc);
+  const size_t unit_index = (size_t)nc * 2 * kslabs + (size_t)sl * units + u;
+  uint8_t* ub = dst + image * image_stride + unit_index * UNIT_BYTES;
+  const uint32_t off = sw128_offset(n_in, k_in);
+  *reinterpret_cast<__nv_bfloat16*>(ub + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(ub + SLAB_BYTES + off) = lo;
+}
+
+inline size_t tc_operand_blob_bytes(int kslabs, int nunits) { return (size_t)kslabs * nunits * UNIT_BYTES; }
+
+template <class Src>
+static int tc_pack_operand(uint8_t* dst, int images, int N, int K, size_t image_stride, const Src& src,
+                           cudaStream_t st) {
+  const int kslabs = (K + KSLAB - 1) / KSLAB, nunits = (N + UNIT_N - 1) / UNIT_N;
+  const long long per_image = (long long)kslabs * nunits * UNIT_N * KSLAB;
+  dim3 grid(cdiv(per_image, 256), images);
+  CIAOSR_LAUNCH((tc_pack_operand_kernel<Src>), grid, 256, 0, st, dst, N, K, kslabs, nunits, image_stride, src);
+  return CIAOSR_OK;
+}
+
+}  // namespace ciaosr

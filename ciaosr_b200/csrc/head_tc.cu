@@ -23,174 +23,10 @@
 // Hidden activations never leave the SM.  Weights stream from L2 (2.2 MB per 128 rows at C=64).
 #include "kernels.cuh"
 #include "pairs.cuh"
-#include "tc_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace ciaosr {
 using namespace tc;
-
-// ---- static smem layout (bytes) --------------------------------------------------------------
-constexpr int SM_A_HI = 0;                              // 4 slabs
-constexpr int SM_A_LO = 4 * SLAB_BYTES;                 // 4 slabs
-constexpr int SM_W = 8 * SLAB_BYTES;                    // 2 ring stages x (hi, lo)
-constexpr int W_STAGES = 2;
-constexpr int SM_CONST = SM_W + W_STAGES * UNIT_BYTES;  // floats: per-kernel constants
-constexpr int CONST_FLOATS = 16 * HID;
-constexpr int SM_BAR = SM_CONST + CONST_FLOATS * 4;
-// barriers (8 B each): W_full[2] W_empty[2] A_ready[4] A_free[4] D_ready[2] D_free[2]; then tmem slot
-constexpr int BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_A_READY = 4, BAR_A_FREE = 8, BAR_D_READY = 12,
-              BAR_D_FREE = 14, N_BARS = 16;
-constexpr int SM_TOTAL = SM_BAR + N_BARS * 8 + 16;
-constexpr int TC_THREADS = 256;
-constexpr int EPI_T0 = 128;                             // first epilogue thread
-
-struct TcShared {
-  uint32_t a_hi, a_lo, w, bar, slot;
-  float* consts;
-};
-
-__device__ __forceinline__ TcShared tc_carve(uint8_t* smem) {
-  TcShared s;
-  const uint32_t base = smem_u32(smem);
-  s.a_hi = base + SM_A_HI; s.a_lo = base + SM_A_LO; s.w = base + SM_W;
-  s.bar = base + SM_BAR; s.slot = base + SM_BAR + N_BARS * 8;
-  s.consts = reinterpret_cast<float*>(smem + SM_CONST);
-  return s;
-}
-__device__ __forceinline__ uint32_t bar_at(const TcShared& s, int i) { return s.bar + 8u * i; }
-
-// common prologue: barrier init + TMEM allocation; returns the TMEM base address
-__device__ __forceinline__ uint32_t tc_prologue(const TcShared& s, uint8_t* smem) {
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_at(s, BAR_W_FULL + i), 1); mbar_init(bar_at(s, BAR_W_EMPTY + i), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_at(s, BAR_A_READY + i), 128); mbar_init(bar_at(s, BAR_A_FREE + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_at(s, BAR_D_READY + i), 1); mbar_init(bar_at(s, BAR_D_FREE + i), 128); }
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(s.slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  return *reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + N_BARS * 8);
-}
-__device__ __forceinline__ void tc_epilogue_dealloc(uint32_t tmem_base) {
-  tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ---- weight producer (warp 0; the whole warp walks the loop, lane 0 issues) -------------------------
-__device__ __forceinline__ void producer_loop(const TcShared& s, const uint8_t* blob, int units_per_tile,
-                                              int n_tiles) {
-  const bool leader = (threadIdx.x & 31) == 0;
-  int stage = 0; uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    for (int u = 0; u < units_per_tile; ++u) {
-      mbar_wait(bar_at(s, BAR_W_EMPTY + stage), phase ^ 1, 100);
-      if (leader) {
-        mbar_arrive_expect_tx(bar_at(s, BAR_W_FULL + stage), UNIT_BYTES);
-        const uint8_t* src = blob + (size_t)u * UNIT_BYTES;
-        const uint32_t dst = s.w + stage * UNIT_BYTES;
-        bulk_g2s(dst, src, SLAB_BYTES, bar_at(s, BAR_W_FULL + stage));
-        bulk_g2s(dst + SLAB_BYTES, src + SLAB_BYTES, SLAB_BYTES, bar_at(s, BAR_W_FULL + stage));
-      }
-      __syncwarp();
-      if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-    }
-  }
-}
-
-// ---- UMMA issuer (warp 1; the whole warp walks the loop, lane 0 issues and commits) -------------------
-struct MmaState { int stage; uint32_t wphase; uint32_t jobctr; uint32_t aready_bits; };
-
-// one job: D[jobctr & 1][:, 0 : 128*units) = A (nslabs x 64 K) * W^T ; A slabs cycle through the 4 smem slots
-__device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, MmaState& m, int nslabs,
-                                        int units, bool a_new) {
-  constexpr uint32_t IDESC = make_idesc_bf16(ROWS, UNIT_N);
-  const bool leader = (threadIdx.x & 31) == 0;
-  const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
-  mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
-  tc_fence_after();
-  for (int sl = 0; sl < nslabs; ++sl) {
-    const int slot = sl & 3;
-    if (a_new) {
-      mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
-      m.aready_bits ^= 1u << slot;
-      tc_fence_after();
-    }
-    const uint32_t a_hi = s.a_hi + slot * SLAB_BYTES, a_lo = s.a_lo + slot * SLAB_BYTES;
-    for (int u = 0; u < units; ++u) {
-      mbar_wait(bar_at(s, BAR_W_FULL + m.stage), m.wphase, 220);
-      tc_fence_after();
-      const uint32_t w_hi = s.w + m.stage * UNIT_BYTES, w_lo = w_hi + SLAB_BYTES;
-      const uint32_t dcol = tmem_base + d * 256 + u * UNIT_N;
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ah = make_desc_sw128(a_hi + ks * 32), al = make_desc_sw128(a_lo + ks * 32);
-          const uint64_t bh = make_desc_sw128(w_hi + ks * 32), bl = make_desc_sw128(w_lo + ks * 32);
-          umma_bf16(dcol, al, bh, IDESC, (sl | ks) != 0 ? 1u : 0u);   // small terms first
-          umma_bf16(dcol, ah, bl, IDESC, 1u);
-          umma_bf16(dcol, ah, bh, IDESC, 1u);
-        }
-        umma_commit(bar_at(s, BAR_W_EMPTY + m.stage));
-      }
-      __syncwarp();
-      if (++m.stage == W_STAGES) { m.stage = 0; m.wphase ^= 1; }
-    }
-    if (leader) umma_commit(bar_at(s, BAR_A_FREE + slot));
-    __syncwarp();
-  }
-  if (leader) umma_commit(bar_at(s, BAR_D_READY + d));
-  __syncwarp();
-  ++m.jobctr;
-}
-
-// ---- epilogue-side helpers (threads 128..255, one row each) -----------------------------------------
-struct EpiState { uint32_t jobctr; uint32_t afree_bits; };   // afree_bits: parity to wait on next, per slot
-
-__device__ __forceinline__ void slab_begin(const TcShared& s, EpiState& e, int slot, bool wait_free) {
-  if (wait_free) {
-    mbar_wait(bar_at(s, BAR_A_FREE + slot), (e.afree_bits >> slot) & 1, 300 + slot);
-  }
-  e.afree_bits ^= 1u << slot;
-}
-__device__ __forceinline__ void slab_done(const TcShared& s, int slot) {
-  fence_proxy_async();
-  mbar_arrive(bar_at(s, BAR_A_READY + slot));
-}
-__device__ __forceinline__ uint32_t epi_wait_d(const TcShared& s, EpiState& e) {
-  const uint32_t d = e.jobctr & 1, n = e.jobctr >> 1;
-  mbar_wait(bar_at(s, BAR_D_READY + d), n & 1, 310);
-  tc_fence_after();
-  return d;
-}
-__device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
-  tc_fence_before();
-  mbar_arrive(bar_at(s, BAR_D_FREE + (e.jobctr & 1)));
-  ++e.jobctr;
-}
-
-// hidden layer epilogue: next A = relu(D + bias), written slab by slab
-template <bool WAIT_FREE>
-__device__ __forceinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t lane_taddr, int row,
-                                           const float* __restrict__ bias_s) {
-  const uint32_t d = epi_wait_d(s, e);
-#pragma unroll 1
-  for (int sl = 0; sl < 4; ++sl) {
-    slab_begin(s, e, sl, WAIT_FREE);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      tmem_ld32(lane_taddr + d * 256 + sl * 64 + half * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias_s[sl * 64 + half * 32 + i], 0.0f);
-      a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    }
-    slab_done(s, sl);
-  }
-  epi_release_d(s, e);
-}
 
 // =====================================================================================================
 // pair kernel
@@ -480,7 +316,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) query_mlp_kernel(const QueryPar
 // blob layout (bytes): [pair units][query units]; a unit = 128 weight rows x 64 K as two SW128 slabs (hi, lo)
 struct TcLayout {
   int Dvp, units5, pair_units, slabs1, query_units;
+  int slabs_k, slabs_v;              // K-slabs of the LR-resolution GEMMs (9C and Dv)
   size_t pair_blob, query_blob;      // byte offsets in the blob
+  size_t k1_blob, v1_blob, kfin_blob;   // layer-1 hoists and the key fold, N = 256 each
   size_t pair_consts, bv5p, query_consts;   // byte offsets (float arrays)
   size_t total;
 };
@@ -496,6 +334,11 @@ static TcLayout tc_layout(int C, int Cn) {
   size_t off = 0;
   t.pair_blob = off; off += (size_t)t.pair_units * UNIT_BYTES;
   t.query_blob = off; off += (size_t)t.query_units * UNIT_BYTES;
+  t.slabs_k = (9 * C + KSLAB - 1) / KSLAB;
+  t.slabs_v = (Dv + KSLAB - 1) / KSLAB;
+  t.k1_blob = off; off += (size_t)t.slabs_k * 2 * UNIT_BYTES;
+  t.v1_blob = off; off += (size_t)t.slabs_v * 2 * UNIT_BYTES;
+  t.kfin_blob = off; off += (size_t)t.slabs_k * 2 * UNIT_BYTES;
   t.pair_consts = off; off += CONST_FLOATS * 4;
   t.bv5p = off; off += (size_t)t.Dvp * 4;
   t.query_consts = off; off += 8 * HID * 4;
@@ -522,7 +365,7 @@ size_t tc_blob_bytes(const ciaosr_head_desc* d) {
 //   W row-major [n_valid_src, ld];  perm_rows / perm_cols: tap-major -> reference channel order.
 __global__ void tc_pack_job_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int ld,
                                    int n_valid, int k_valid, int nslabs, int units, int n0, int perm_rows,
-                                   int perm_cols, int C) {
+                                   int perm_cols, int C, int trans) {
   const long long total = (long long)nslabs * units * UNIT_N * KSLAB;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -536,7 +379,7 @@ __global__ void tc_pack_job_kernel(uint8_t* __restrict__ dst, const float* __res
     const int Dk = 9 * C;
     const int ns = (perm_rows && n < Dk) ? (n % C) * 9 + n / C : n;
     const int ks = (perm_cols && k < Dk) ? (k % C) * 9 + k / C : k;
-    w = W[(long long)ns * ld + ks];
+    w = trans ? W[(long long)ks * ld + ns] : W[(long long)ns * ld + ks];   // trans: W is [K, N]
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
@@ -570,10 +413,10 @@ int tc_pack(const ciaosr_head_desc* d, const PlanLayout& L, float* plan, cudaStr
   const TcLayout t = tc_layout(L.C, L.Cn);
   uint8_t* blob = reinterpret_cast<uint8_t*>(plan + L.tc_blob);
   auto pack = [&](uint8_t* dst, const float* W, int ld, int n_valid, int k_valid, int nslabs, int units,
-                  int n0, int pr, int pcol) -> int {
+                  int n0, int pr, int pcol, int trans = 0) -> int {
     const long long total = (long long)nslabs * units * UNIT_N * KSLAB;
     CIAOSR_LAUNCH(tc_pack_job_kernel, cdiv(total, 256), 256, 0, st, dst, W, ld, n_valid, k_valid, nslabs,
-                  units, n0, pr, pcol, L.C);
+                  units, n0, pr, pcol, L.C, trans);
     return CIAOSR_OK;
   };
   int rc;
@@ -598,11 +441,115 @@ int tc_pack(const ciaosr_head_desc* d, const PlanLayout& L, float* plan, cudaStr
     if ((rc = pack(p, d->imnet_q.weight[l], HID, HID, HID, 4, 2, 0, 0, 0))) return rc;
     p += (size_t)8 * UNIT_BYTES;
   }
+  // LR-resolution GEMM operands: layer-1 hoists W1[:, :D] (tap-major K) and the key fold W5k^T
+  if ((rc = pack(blob + t.k1_blob, d->imnet_k.weight[0], L.Dk + 4, HID, L.Dk, t.slabs_k, 2, 0, 0, 1))) return rc;
+  if ((rc = pack(blob + t.v1_blob, d->imnet_v.weight[0], L.Dv + 4, HID, L.Dv, t.slabs_v, 2, 0, 0, 1))) return rc;
+  if ((rc = pack(blob + t.kfin_blob, d->imnet_k.weight[4], HID, HID, L.Dk, t.slabs_k, 2, 0, 0, 1, 1))) return rc;
   const int n = t.Dvp > 4 * HID ? t.Dvp : 4 * HID;
   CIAOSR_LAUNCH(tc_pack_consts_kernel, cdiv(n, 256), 256, 0, st,
                 reinterpret_cast<float*>(blob + t.pair_consts), reinterpret_cast<float*>(blob + t.bv5p),
                 reinterpret_cast<float*>(blob + t.query_consts), plan, L, t.Dvp, d->imnet_q.weight[4],
                 d->imnet_q.bias[4]);
+  return CIAOSR_OK;
+}
+
+// =====================================================================================================
+// LR-resolution precompute on the tensor cores (replaces run_lr_precompute's CUDA-core GEMMs)
+// =====================================================================================================
+struct UnfoldGen {       // A[pix, kp] = tap-major 3x3 unfold of the NHWC feature (+ non-local channels)
+  const float* f; const float* nl; int H, W, C, Cn, K;
+  struct Row { int y, x; };
+  __device__ __forceinline__ Row row(long long m) const {
+    const int hw = (int)(m % ((long long)H * W));
+    return Row{hw / W, hw % W};
+  }
+  __device__ __forceinline__ void fill(Row& r, long long m, int k0, float (&v)[32]) const {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < 9 * C) {
+        const int t = k / C, ch = k - t * C;
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        if (r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W)
+          q = __ldg(reinterpret_cast<const float4*>(f + (m + dy * W + dx) * C + ch));
+      } else if (k < K) {
+        q = __ldg(reinterpret_cast<const float4*>(nl + m * Cn + (k - 9 * C)));
+      }
+      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+  }
+};
+struct PairProdGen {     // A[pix*9 + d, kp] = U[pix, kp] * U[pix + d, kp];  also c0 = sum_kp A * b5[kp]
+  const float* f; const float* fin; int H, W, C, ldfin;     // fin[kp * ldfin + 256] = permuted last-layer bias
+  struct Row { int y, x, dy, dx; long long pix; bool ok; float c0; };
+  __device__ __forceinline__ Row row(long long m) const {
+    Row r;
+    r.pix = m / 9;
+    const int d = (int)(m % 9), hw = (int)(r.pix % ((long long)H * W));
+    r.y = hw / W; r.x = hw % W; r.dy = d / 3 - 1; r.dx = d % 3 - 1;
+    r.ok = r.y + r.dy >= 0 && r.y + r.dy < H && r.x + r.dx >= 0 && r.x + r.dx < W;
+    r.c0 = 0.0f;
+    return r;
+  }
+  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r.ok && k < 9 * C) {
+        const int t = k / C, ch = k - t * C;
+        const int ty = t / 3 - 1, tx = t % 3 - 1;
+        const int ay = r.y + ty, ax = r.x + tx, by = ay + r.dy, bx = ax + r.dx;
+        if (ay >= 0 && ay < H && ax >= 0 && ax < W && by >= 0 && by < H && bx >= 0 && bx < W) {
+          const float* pa = f + (r.pix + ty * W + tx) * C + ch;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(pa));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(pa + (r.dy * W + r.dx) * C));
+          q = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+          r.c0 = fmaf(q.x, __ldg(fin + (long long)k * ldfin + HID), r.c0);
+          r.c0 = fmaf(q.y, __ldg(fin + (long long)(k + 1) * ldfin + HID), r.c0);
+          r.c0 = fmaf(q.z, __ldg(fin + (long long)(k + 2) * ldfin + HID), r.c0);
+          r.c0 = fmaf(q.w, __ldg(fin + (long long)(k + 3) * ldfin + HID), r.c0);
+        }
+      }
+      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+  }
+};
+template <class Row>
+struct StoreRowsEpi {    // C[m, n0 .. n0+32) = v   (ld % 4 == 0)
+  float* c; int ld;
+  __device__ __forceinline__ void store(const Row&, long long m, int n0, const float (&v)[32]) const {
+    float4* dst = reinterpret_cast<float4*>(c + m * ld + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+};
+struct StoreGEpi {       // G rows: 256 folded weights + the folded bias term in column 256
+  float* g; int ld;
+  __device__ __forceinline__ void store(const PairProdGen::Row& r, long long m, int n0, const float (&v)[32]) const {
+    float4* dst = reinterpret_cast<float4*>(g + m * ld + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    if (n0 == HID - 32) g[m * ld + HID] = r.c0;
+  }
+};
+
+static int run_lr_precompute_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, float* Pk, float* Pv,
+                                float* G, int ldg, cudaStream_t st) {
+  const TcLayout t = tc_layout(L.C, L.Cn);
+  const uint8_t* blob = reinterpret_cast<const uint8_t*>(plan + L.tc_blob);
+  const long long npix = (long long)a.B * a.H * a.W;
+  int rc;
+  UnfoldGen uk{a.featT, a.nlT, a.H, a.W, L.C, L.Cn, L.Dk};
+  UnfoldGen uv{a.featT, a.nlT, a.H, a.W, L.C, L.Cn, L.Dv};
+  if ((rc = tc_gemm(GemmShape{npix, t.slabs_k, 2, npix, 0}, blob + t.k1_blob, uk,
+                    StoreRowsEpi<UnfoldGen::Row>{Pk, HID}, st))) return rc;
+  if ((rc = tc_gemm(GemmShape{npix, t.slabs_v, 2, npix, 0}, blob + t.v1_blob, uv,
+                    StoreRowsEpi<UnfoldGen::Row>{Pv, HID}, st))) return rc;
+  PairProdGen pg{a.featT, plan + L.k.fin, a.H, a.W, L.C, HID + 1};
+  if ((rc = tc_gemm(GemmShape{npix * 9, t.slabs_k, 2, npix * 9, 0}, blob + t.kfin_blob, pg, StoreGEpi{G, ldg}, st)))
+    return rc;
   return CIAOSR_OK;
 }
 
@@ -647,7 +594,7 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
   int rc;
   {
     StageScope sc(2, st);
-    if ((rc = run_lr_precompute(L, plan, a, b.Pk, b.Pv, b.G, tc_ldg(), st))) return rc;
+    if ((rc = run_lr_precompute_tc(L, plan, a, b.Pk, b.Pv, b.G, tc_ldg(), st))) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {

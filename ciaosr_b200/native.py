@@ -123,19 +123,21 @@ class HeadPlan:
         return _lib.load().ciaosr_engine_supported(ctypes.byref(self.desc), ENGINES[engine]) == 1
 
     # -- calls ---------------------------------------------------------------------
-    def cross_scale_attention(self, feature):
+    def cross_scale_attention(self, feature, engine="auto"):
         """feature [B,C,H,W] -> [B,Cn,H,W] (CrossScaleAttention.forward)."""
         feature = _f32c(feature, "feature")
         B, C, H, W = feature.shape
         if C != self.channels:
             raise ValueError(f"feature has {C} channels, head was built for {self.channels}")
         out = torch.empty(B, self.n_nonlocal, H, W, dtype=torch.float32, device=feature.device)
-        nbytes = self.workspace_bytes(B, H, W, 0, "simt")
-        ws = self._workspace(nbytes)
+        n = ctypes.c_size_t(0)
+        _lib.check(_lib.load().ciaosr_cross_scale_attn_workspace_bytes(
+            ctypes.byref(self.desc), B, H, W, ENGINES[engine], ctypes.byref(n)))
+        ws = self._workspace(n.value)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().ciaosr_cross_scale_attn_forward(
-                ctypes.byref(self.desc), _ptr(self.buf), _ptr(feature), B, H, W, _ptr(out),
-                _ptr(ws), ws.numel(), _stream(self.device)))
+                ctypes.byref(self.desc), _ptr(self.buf), _ptr(feature), B, H, W, ENGINES[engine],
+                _ptr(out), _ptr(ws), ws.numel(), _stream(self.device)))
         return out
 
     def query_rgb(self, feature, coord, cell, lr_image=None, nonlocal_feat=None, eval_bsize=None,

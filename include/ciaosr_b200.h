@@ -139,9 +139,12 @@ int ciaosr_workspace_bytes(const ciaosr_head_desc* desc, int B, int H, int W,
                            int q, int engine, size_t* bytes);
 
 /* ---- cross-scale attention --------------------------------------------- */
-/* feature [B,C,H,W] NCHW -> out [B,C*n_scales,H,W] NCHW.                    */
+/* feature [B,C,H,W] NCHW -> out [B,C*n_scales,H,W] NCHW.  engine: AUTO uses the
+ * tensor-core path when C % 8 == 0, SIMT forces the fp32 CUDA-core path.     */
+int ciaosr_cross_scale_attn_workspace_bytes(const ciaosr_head_desc* desc, int B, int H, int W,
+                                            int engine, size_t* bytes);
 int ciaosr_cross_scale_attn_forward(const ciaosr_head_desc* desc, const void* plan,
-                                    const float* feature, int B, int H, int W,
+                                    const float* feature, int B, int H, int W, int engine,
                                     float* out, void* workspace, size_t workspace_bytes,
                                     void* stream);
 

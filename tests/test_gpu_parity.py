@@ -32,9 +32,13 @@ def test_cross_scale_attention_golden(name):
     holder.cs_attn = CrossScaleAttention(channel=meta["c"], scale=[2])
     synth.fill_module(holder, meta["seed"])
     holder = holder.to(_dev())
-    out = holder.cs_attn(a["feature"].to(_dev())).cpu()
+    out = holder.cs_attn(a["feature"].to(_dev())).cpu()          # module API, engine auto
     assert out.shape == a["out"].shape
     assert max_abs(out, a["out"]) < TOL
+    plan = holder.cs_attn._plan[1]
+    for engine in ["simt"] + (["tcgen05"] if meta["c"] % 8 == 0 else []):
+        out = plan.cross_scale_attention(a["feature"].to(_dev()), engine=engine).cpu()
+        assert max_abs(out, a["out"]) < TOL, engine
 
 
 @pytest.mark.parametrize("name", HEAD_CASES)
@@ -46,8 +50,8 @@ def test_head_golden(name):
         plan = g.head_plan()
         feat = a["feature"].to(dev)
         if meta["non_local"]:
-            nl = plan.cross_scale_attention(feat).cpu()
-            assert max_abs(nl, a["nonlocal"]) < TOL
+            nl = plan.cross_scale_attention(feat, engine=engine if meta["c"] % 8 == 0 else "simt").cpu()
+            assert max_abs(nl, a["nonlocal"]) < TOL, (engine, "cs_attn")
         g.gen_feature = lambda _x, _f=feat: [_f]
         for tag in meta["tags"]:
             coord, cell = a[f"coord_{tag}"].to(dev), a[f"cell_{tag}"].to(dev)

@@ -12,6 +12,10 @@ for name in ["head_c64", "head_c64_nonl0"]:
         if not g.head_plan().engine_supported(engine):
             print(name, engine, "unsupported"); continue
         feat = a["feature"].to(dev)
+        if meta["non_local"]:
+            nl = g.head_plan().cross_scale_attention(feat, engine=engine)
+            print(f"{name} {engine} cs_attn: max-abs {(nl.cpu() - a['nonlocal']).abs().max():.3e} "
+                  f"scale {a['nonlocal'].abs().mean():.3f}", flush=True)
         for tag in meta["tags"]:
             coord, cell = a[f"coord_{tag}"].to(dev), a[f"cell_{tag}"].to(dev)
             try:
