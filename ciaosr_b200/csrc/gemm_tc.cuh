@@ -25,32 +25,34 @@ struct GemmShape {
 // AGen:  struct Row;  __device__ Row row(long long m) const;
 //        __device__ void fill(Row&, long long m, int k0, float (&v)[32]) const;     (k0 % 32 == 0)
 // Epi:   __device__ void store(const typename AGen::Row&, long long m, int n0, const float (&v)[32]) const;
+constexpr int TC_THREADS = 256;      // 4 control warps + 128 row threads
+
 template <class AGen, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcShared s = tc_carve(smem);
-  const uint32_t tmem_base = tc_prologue(s, smem);
+  const uint32_t tmem_base = tc_prologue<1, 128>(s, smem);
   const int warp = threadIdx.x >> 5;
   const int m_tiles = (int)((g.M + ROWS - 1) / ROWS);
   const int n_chunks = (g.nunits + 1) / 2;
   const long long n_jobs = (long long)m_tiles * n_chunks;
 
   if (warp == 0) {
-    ProdState ps{0, 0};
+    ProdState ps{0, 0, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
       const int units = min(2, g.nunits - 2 * nc);
       const long long image = ((long long)mt * ROWS) / g.rows_per_image;
       // blob order: for chunk: for slab: for unit
       const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES;
-      produce_units(s, ps, src, g.kslabs * units);
+      produce_units<1>(s, ps, src, g.kslabs * units, 0);
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int nc = (int)(job % n_chunks);
-      mma_job(s, tmem_base, m, g.kslabs, min(2, g.nunits - 2 * nc), true);
+      mma_job<1>(s, tmem_base, m, g.kslabs, min(2, g.nunits - 2 * nc), true);
     }
   } else if (warp >= 4) {
     const int row = threadIdx.x - EPI_T0;
@@ -88,7 +90,7 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
       epi_release_d(s, e);
     }
   }
-  tc_epilogue_dealloc(tmem_base);
+  tc_teardown<1>(tmem_base);
 }
 
 inline int tc_grid_size(long long n_jobs) {

@@ -1,314 +1,29 @@
 // tcgen05 engine for the implicit attention head (CIAOSR_ENGINE_TCGEN05), sm_100a.
 //
-// Two persistent, warp-specialised kernels run the MLP stacks on the 5th-gen tensor cores
-// with fp32-grade accuracy (bf16 hi/lo split, 3 UMMAs per product, fp32 accumulation in TMEM):
+// Persistent, warp-specialised kernels run every dense contraction of the head on the 5th-gen tensor
+// cores with fp32-grade accuracy (bf16 hi/lo split, 3 UMMAs per product, fp32 accumulation in TMEM):
 //
+//   LR precompute     tc_gemm_kernel (gemm_tc.cuh): layer-1 hoists Pk, Pv and the key fold G
 //   pair_mlp_kernel   per 128 (query, neighbour) rows = 32 queries x 4 neighbours:
-//       layer 1 of imnet_k / imnet_v from the LR-resolution hoist (gather + 4 FMAs, ciaosr_net.py:195-205)
+//       layer 1 of imnet_k / imnet_v from the hoist (gather + 4 FMAs, ciaosr_net.py:195-205)
 //       hidden layers 2..4 of both MLPs on UMMA (M=128, N=256, K=256 each)
 //       key side: logit = h4k . G[query px, offset] (+c0), softmax over the 4 neighbours (:203,:214-215)
 //       value side: last Linear (256 -> Dv) on UMMA in N-chunks, fused with  sum_n a_n * value_n * W_v  (:206,:215)
 //       -> x[query, Dv]
 //   query_mlp_kernel  per 128 queries: imnet_q (Dv -> 256 x4 -> 3) + bilinear residual (:221, :107-108)
 //
-// Pipeline inside a CTA (1 CTA / SM, all 512 TMEM columns = two 128x256 fp32 accumulators):
-//   warp 0  weight producer: cp.async.bulk (TMA engine) of pre-swizzled 32 KB weight units into a 2-stage ring
-//   warp 1  UMMA issuer (one lane): waits operand slabs / weight units, issues tcgen05.mma, commits to mbarriers
-//   warp 2  TMEM allocator
-//   warps 4-7  one thread per row: build layer-1 operands, drain accumulators (tcgen05.ld),
-//              bias+ReLU, bf16 hi/lo split, write the next layer's A operand straight into the
-//              128B-swizzled K-major smem slabs the next UMMA reads.  Slab-granular mbarriers let layer
-//              l+1's UMMAs start as soon as the first 64 columns of layer l are converted, while the
-//              second accumulator absorbs them.
-// Hidden activations never leave the SM.  Weights stream from L2 (2.2 MB per 128 rows at C=64).
+// Pipeline (tc_pipeline.cuh): 1 CTA / SM, all 512 TMEM columns = two 128x256 fp32 accumulators; warp 0
+// streams pre-swizzled 16 KB weight slabs through a 4-stage ring with cp.async.bulk (TMA engine), warp 1
+// issues tcgen05.mma / tcgen05.commit, row threads drain accumulators with tcgen05.ld, apply bias+ReLU,
+// split to bf16 hi/lo and write the next layer's A operand straight into the 128B-swizzled K-major smem
+// slabs the next UMMA reads.  Slab-granular mbarriers let layer l+1's UMMAs start as soon as the first 64
+// columns of layer l are converted, while the second accumulator absorbs them.  Hidden activations never
+// leave the SM.  In the two head kernels CTA pairs (2-CTA clusters) share one weight stream: each CTA
+// loads half of every unit and multicasts it to both, halving L2 reads.
 #include "kernels.cuh"
-#include "pairs.cuh"
-#include "gemm_tc.cuh"
+#include "tc_head_kernels.cuh"
 
 namespace ciaosr {
-using namespace tc;
-
-// =====================================================================================================
-// pair kernel
-// =====================================================================================================
-struct PairParams {
-  PairConsts pc;
-  const float* coord; const float* cell;
-  const float* featT; const float* nlT;
-  int C, Cn, Dv, Dvp;
-  const float* Pk; const float* Pv; const float* G; int ldg;
-  const float* consts;        // 16 x 256 floats, see pair_consts layout below
-  const float* bv5p;          // [Dvp] last-layer value bias, tap-major, zero padded
-  const uint8_t* blob; int units_per_tile; int units5;
-  float* x;                   // [total_q, Dvp]
-  long long total_rows; int n_tiles;
-  float softmax_scale;
-};
-// consts layout (x256 floats): 0..3 rc_k, 4 b1_k, 5..7 b_k(layers 2..4), 8..11 rc_v, 12 b1_v, 13..15 b_v(2..4)
-
-__device__ __forceinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, const PairInfo& p,
-                                           const float* __restrict__ P, const float* __restrict__ rc_s,
-                                           const float* __restrict__ b1_s) {
-  const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) : nullptr;
-#pragma unroll 1
-  for (int sl = 0; sl < 4; ++sl) {
-    slab_begin(s, e, sl, false);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      const int c0 = sl * 64 + half * 32;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 q = prow ? __ldg(prow + (c0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = c0 + i;
-        float t = v[i] + b1_s[c];
-        t = fmaf(rc_s[c], p.rel_y, t);
-        t = fmaf(rc_s[HID + c], p.rel_x, t);
-        t = fmaf(rc_s[2 * HID + c], p.sc_y, t);
-        t = fmaf(rc_s[3 * HID + c], p.sc_x, t);
-        v[i] = fmaxf(t, 0.0f);
-      }
-      a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    }
-    slab_done(s, sl);
-  }
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1) pair_mlp_kernel(const PairParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
-  for (int i = threadIdx.x; i < CONST_FLOATS; i += TC_THREADS) s.consts[i] = P.consts[i];
-  const uint32_t tmem_base = tc_prologue(s, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks5 = (P.units5 + 1) / 2;
-
-  if (warp == 0) {
-    producer_loop(s, P.blob, P.units_per_tile, P.n_tiles);
-  } else if (warp == 1) {
-    MmaState m{0, 0, 0, 0};
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      for (int j = 0; j < 6; ++j) mma_job(s, tmem_base, m, 4, 2, true);
-      for (int c = 0; c < nchunks5; ++c) mma_job(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
-    }
-  } else if (warp >= 4) {
-    const int row = threadIdx.x - EPI_T0;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0};
-    const float* cst = s.consts;
-    const int C = P.C, H = P.pc.H, W = P.pc.W;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      const long long R = (long long)tile * ROWS + row;
-      const bool valid = R < P.total_rows;
-      PairInfo p;
-      if (valid) p = compute_pair(P.pc, P.coord, P.cell, R >> 2, (int)(R & 3));
-      else { p.pix = -1; p.gidx = -1; p.rel_y = p.rel_x = p.sc_y = p.sc_x = 0.0f; }
-
-      // ---- key chain -----------------------------------------------------------------------
-      gen_layer1(s, e, row, p, P.Pk, cst, cst + 4 * HID);
-      epi_hidden<false>(s, e, lane_taddr, row, cst + 5 * HID);
-      epi_hidden<false>(s, e, lane_taddr, row, cst + 6 * HID);
-      float logit = 0.0f;
-      {
-        const uint32_t d = epi_wait_d(s, e);
-        const float* bias_s = cst + 7 * HID;
-        const float4* grow = p.gidx >= 0 ? reinterpret_cast<const float4*>(P.G + (long long)p.gidx * P.ldg) : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HID; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_taddr + d * 256 + c0, v);
-          if (grow) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 g = __ldg(grow + (c0 >> 2) + j);
-              logit = fmaf(fmaxf(v[4 * j] + bias_s[c0 + 4 * j], 0.0f), g.x, logit);
-              logit = fmaf(fmaxf(v[4 * j + 1] + bias_s[c0 + 4 * j + 1], 0.0f), g.y, logit);
-              logit = fmaf(fmaxf(v[4 * j + 2] + bias_s[c0 + 4 * j + 2], 0.0f), g.z, logit);
-              logit = fmaf(fmaxf(v[4 * j + 3] + bias_s[c0 + 4 * j + 3], 0.0f), g.w, logit);
-            }
-          }
-        }
-        if (grow) logit += __ldg(P.G + (long long)p.gidx * P.ldg + HID);
-        epi_release_d(s, e);
-      }
-      // softmax over the 4 neighbours of this query (4 adjacent lanes)
-      float a;
-      {
-        const float l = __fdiv_rn(logit, P.softmax_scale);
-        float mx = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float ex = expf(l - mx);
-        float sum = ex + __shfl_xor_sync(0xffffffffu, ex, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        a = valid ? __fdiv_rn(ex, sum) : 0.0f;
-      }
-
-      // ---- value chain -----------------------------------------------------------------------
-      gen_layer1(s, e, row, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
-      epi_hidden<false>(s, e, lane_taddr, row, cst + 13 * HID);
-      epi_hidden<false>(s, e, lane_taddr, row, cst + 14 * HID);
-      epi_hidden<false>(s, e, lane_taddr, row, cst + 15 * HID);   // h4v -> operand of the last Linear
-
-      // geometry of this row's latent code for the value gather
-      int py = 0, px = 0;
-      const float* fbase = nullptr;
-      const float* nbase = nullptr;
-      if (p.pix >= 0) {
-        const int hw = p.pix % (H * W);
-        py = hw / W; px = hw % W;
-        fbase = P.featT + (long long)p.pix * C;
-        if (P.nlT) nbase = P.nlT + (long long)p.pix * P.Cn;
-      }
-      const long long q = R >> 2;
-      const int sub = (lane & 1) * 16 + ((lane >> 1) & 1) * 8;   // columns of a 32-chunk this lane ends up owning
-      for (int c = 0; c < nchunks5; ++c) {
-        const int units = min(2, P.units5 - 2 * c);
-        const uint32_t d = epi_wait_d(s, e);
-#pragma unroll 1
-        for (int cc = 0; cc < units * 4; ++cc) {
-          const int cp0 = c * 256 + cc * 32;
-          float v[32];
-          tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int cp = cp0 + 4 * g;
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (fbase != nullptr && cp < P.Dv) {
-              if (cp < 9 * C) {
-                const int t = cp / C, ch = cp - t * C;
-                const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                  val = __ldg(reinterpret_cast<const float4*>(fbase + ((t / 3 - 1) * W + (t % 3 - 1)) * C + ch));
-              } else {
-                val = __ldg(reinterpret_cast<const float4*>(nbase + (cp - 9 * C)));
-              }
-            }
-            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bv5p + cp));
-            v[4 * g] = a * val.x * (v[4 * g] + b.x);
-            v[4 * g + 1] = a * val.y * (v[4 * g + 1] + b.y);
-            v[4 * g + 2] = a * val.z * (v[4 * g + 2] + b.z);
-            v[4 * g + 3] = a * val.w * (v[4 * g + 3] + b.w);
-          }
-          // sum over the 4 neighbour rows (lanes 4q..4q+3), leaving each lane with 8 of the 32 columns
-          float r16[16], r8[8];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float keep = (lane & 1) ? v[16 + i] : v[i];
-            const float send = (lane & 1) ? v[i] : v[16 + i];
-            r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float keep = (lane & 2) ? r16[8 + i] : r16[i];
-            const float send = (lane & 2) ? r16[i] : r16[8 + i];
-            r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-          }
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(P.x + q * P.Dvp + cp0 + sub);
-            dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
-            dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
-          }
-        }
-        epi_release_d(s, e);
-      }
-    }
-  }
-  tc_epilogue_dealloc(tmem_base);
-}
-
-// =====================================================================================================
-// query kernel: imnet_q + residual
-// =====================================================================================================
-struct QueryParams {
-  const float* x; int Dvp;                 // [total_q, Dvp]
-  const float* consts;                     // x256 floats: 0..3 b_q(layers 1..4), 4..6 W5 rows, 7: b5 in [0..3)
-  const uint8_t* blob; int units_per_tile; int slabs1;
-  const float* lr; const float* coord; int H, W, Q;
-  float* out; long long total_q; int n_tiles;
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 1) query_mlp_kernel(const QueryParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
-  for (int i = threadIdx.x; i < 8 * HID; i += TC_THREADS) s.consts[i] = P.consts[i];
-  const uint32_t tmem_base = tc_prologue(s, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0) {
-    producer_loop(s, P.blob, P.units_per_tile, P.n_tiles);
-  } else if (warp == 1) {
-    MmaState m{0, 0, 0, 0};
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      mma_job(s, tmem_base, m, P.slabs1, 2, true);
-      for (int j = 0; j < 3; ++j) mma_job(s, tmem_base, m, 4, 2, true);
-    }
-  } else if (warp >= 4) {
-    const int row = threadIdx.x - EPI_T0;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0xFu};                     // A_free waits start at parity 1 (fresh barrier passes)
-    const float* cst = s.consts;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      const long long g = (long long)tile * ROWS + row;
-      const bool valid = g < P.total_q;
-      const float4* xrow = valid ? reinterpret_cast<const float4*>(P.x + g * P.Dvp) : nullptr;
-      // layer-1 operand: x (fp32) -> bf16 hi/lo slabs, streamed through the 4 slots
-#pragma unroll 1
-      for (int sl = 0; sl < P.slabs1; ++sl) {
-        const int slot = sl & 3;
-        slab_begin(s, e, slot, true);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = xrow ? __ldg(xrow + sl * 16 + half * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-          }
-          a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
-        }
-        slab_done(s, slot);
-      }
-      epi_hidden<true>(s, e, lane_taddr, row, cst);
-      epi_hidden<true>(s, e, lane_taddr, row, cst + HID);
-      epi_hidden<true>(s, e, lane_taddr, row, cst + 2 * HID);
-      // last hidden layer + the 256 -> 3 Linear on CUDA cores
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      {
-        const uint32_t d = epi_wait_d(s, e);
-        const float* bias_s = cst + 3 * HID;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HID; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_taddr + d * 256 + c0, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float h = fmaxf(v[i] + bias_s[c0 + i], 0.0f);
-            o0 = fmaf(h, cst[4 * HID + c0 + i], o0);
-            o1 = fmaf(h, cst[5 * HID + c0 + i], o1);
-            o2 = fmaf(h, cst[6 * HID + c0 + i], o2);
-          }
-        }
-        epi_release_d(s, e);
-      }
-      if (valid) {
-        o0 += cst[7 * HID]; o1 += cst[7 * HID + 1]; o2 += cst[7 * HID + 2];
-        if (P.lr) {
-          const int b = (int)(g / P.Q);
-          const float cy = P.coord[g * 2], cx = P.coord[g * 2 + 1];
-          const float* img = P.lr + (long long)b * 3 * P.H * P.W;
-          o0 += bilinear_border(img, P.H, P.W, cy, cx);
-          o1 += bilinear_border(img + P.H * P.W, P.H, P.W, cy, cx);
-          o2 += bilinear_border(img + 2 * P.H * P.W, P.H, P.W, cy, cx);
-        }
-        P.out[g * 3] = o0; P.out[g * 3 + 1] = o1; P.out[g * 3 + 2] = o2;
-      }
-    }
-  }
-  tc_epilogue_dealloc(tmem_base);
-}
 
 // =====================================================================================================
 // plan-time packing
@@ -339,7 +54,7 @@ static TcLayout tc_layout(int C, int Cn) {
   t.k1_blob = off; off += (size_t)t.slabs_k * 2 * UNIT_BYTES;
   t.v1_blob = off; off += (size_t)t.slabs_v * 2 * UNIT_BYTES;
   t.kfin_blob = off; off += (size_t)t.slabs_k * 2 * UNIT_BYTES;
-  t.pair_consts = off; off += CONST_FLOATS * 4;
+  t.pair_consts = off; off += 16 * HID * 4;     // immediately followed by bv5p: one contiguous const block
   t.bv5p = off; off += (size_t)t.Dvp * 4;
   t.query_consts = off; off += 8 * HID * 4;
   t.total = (off + 255) / 256 * 256;
@@ -348,6 +63,8 @@ static TcLayout tc_layout(int C, int Cn) {
 
 bool tc_shapes_ok(const ciaosr_head_desc* d) {
   if (d->local_size != 2 || d->channels % 4 != 0) return false;
+  const int Cn = d->non_local_attn ? d->channels * d->cs_attn.n_scales : 0;
+  if (9 * d->channels + Cn > 2048 - 127) return false;        // bv5p lives in the 2048-float smem const tail
   const ciaosr_mlp_desc* ms[3] = {&d->imnet_q, &d->imnet_k, &d->imnet_v};
   for (auto m : ms) {
     if (m->n_layers != 5) return false;
@@ -576,11 +293,38 @@ size_t head_tc_workspace(const PlanLayout& L, int B, int H, int W, int Q) {
   return a.used();
 }
 
-static int tc_grid(int n_tiles) {
+// CTAs sharing one weight stream in the head kernels (CIAOSR_TC_CLUSTER=1 disables the multicast)
+static int tc_cluster_size() {
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("CIAOSR_TC_CLUSTER");
+    cl = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return cl;
+}
+static int tc_grid(int n_tiles, int CL) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return n_tiles < sms ? n_tiles : sms;
+  sms = sms / CL * CL;
+  const int want = (n_tiles + CL - 1) / CL * CL;
+  return want < sms ? want : sms;
+}
+template <class Kernel, class Params>
+static int launch_clustered(Kernel kernel, int grid, int CL, cudaStream_t st, const Params& P) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(HEAD_THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, P);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (err != cudaSuccess) {
+    set_error("launch of a clustered tcgen05 kernel failed: %s", cudaGetErrorString(err));
+    return CIAOSR_E_CUDA;
+  }
+  return CIAOSR_OK;
 }
 
 int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void* ws, size_t ws_bytes,
@@ -596,10 +340,13 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     StageScope sc(2, st);
     if ((rc = run_lr_precompute_tc(L, plan, a, b.Pk, b.Pv, b.G, tc_ldg(), st))) return rc;
   }
+  const int CL = tc_cluster_size();
   static bool attr_set = false;
   if (!attr_set) {
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(pair_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(query_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(pair_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(pair_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(query_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(query_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr_set = true;
   }
   const long long total_q = (long long)a.B * a.Q;
@@ -611,11 +358,13 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     P.C = L.C; P.Cn = L.Cn; P.Dv = L.Dv; P.Dvp = t.Dvp;
     P.Pk = b.Pk; P.Pv = b.Pv; P.G = b.G; P.ldg = tc_ldg();
     P.consts = reinterpret_cast<const float*>(blob + t.pair_consts);
-    P.bv5p = reinterpret_cast<const float*>(blob + t.bv5p);
     P.blob = blob + t.pair_blob; P.units_per_tile = t.pair_units; P.units5 = t.units5;
     P.x = b.x; P.total_rows = total_q * 4; P.n_tiles = (int)((P.total_rows + ROWS - 1) / ROWS);
     P.softmax_scale = L.softmax_scale;
-    CIAOSR_LAUNCH(pair_mlp_kernel, tc_grid(P.n_tiles), TC_THREADS, SM_TOTAL, st, P);
+    const int grid = tc_grid(P.n_tiles, CL);
+    P.iters = (P.n_tiles + grid - 1) / grid;
+    int rc2 = CL == 2 ? launch_clustered(pair_mlp_kernel<2>, grid, 2, st, P) : launch_clustered(pair_mlp_kernel<1>, grid, 1, st, P);
+    if (rc2) return rc2;
   }
   {
     StageScope sc(4, st);
@@ -625,7 +374,10 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     Qp.blob = blob + t.query_blob; Qp.units_per_tile = t.query_units; Qp.slabs1 = t.slabs1;
     Qp.lr = a.lr; Qp.coord = a.coord; Qp.H = a.H; Qp.W = a.W; Qp.Q = a.Q;
     Qp.out = a.out; Qp.total_q = total_q; Qp.n_tiles = (int)((total_q + ROWS - 1) / ROWS);
-    CIAOSR_LAUNCH(query_mlp_kernel, tc_grid(Qp.n_tiles), TC_THREADS, SM_TOTAL, st, Qp);
+    const int grid = tc_grid(Qp.n_tiles, CL);
+    Qp.iters = (Qp.n_tiles + grid - 1) / grid;
+    int rc2 = CL == 2 ? launch_clustered(query_mlp_kernel<2>, grid, 2, st, Qp) : launch_clustered(query_mlp_kernel<1>, grid, 1, st, Qp);
+    if (rc2) return rc2;
   }
   return CIAOSR_OK;
 }

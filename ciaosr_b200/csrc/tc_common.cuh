@@ -108,6 +108,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, do other work, then wait (the wait names the registers so that no
+// use of them can be scheduled above it)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// ---- clusters ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy delivered to the same smem offset (and mbarrier offset) of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (ignored for swizzled K-major, 1)
@@ -144,6 +189,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 // ---- bf16 hi/lo split of an fp32 value pair ----------------------------------------------
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the pair carries 16 mantissa bits, and
 // A*W ~= Ahi*Whi + Ahi*Wlo + Alo*Whi is fp32-grade (3 UMMAs per product).
@@ -155,8 +208,9 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 
 // Write 32 consecutive K-columns [c0, c0+32) (c0 % 32 == 0, within one 64-wide slab) of
 // operand row `row` into the hi and lo slabs (SW128: 16-byte chunk j of a row lives at j ^ (row & 7)).
+template <class T>
 __device__ __forceinline__ void a_store32(uint32_t slab_hi, uint32_t slab_lo, int row, int c0,
-                                          const float (&v)[32]) {
+                                          const T (&v)[32]) {
   const uint32_t rbase = (uint32_t)row * 128u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {

@@ -1,0 +1,363 @@
+// The two fused tcgen05 kernels of the head (see head_tc.cu for the engine overview).
+//
+// Thread layout of both kernels: 384 threads = 4 control warps (0 weight producer, 1 UMMA issuer,
+// 2 TMEM allocator, 3 idle) + 8 row warps.  Two threads serve each of the 128 rows of a tile:
+// thread (half h, lane-quarter q, lane l) <-> row 32 q + l, columns [32 h, 32 h + 32) of every 64-column
+// slab (warps 4-7 are h = 0, warps 8-11 are h = 1; a warp may only touch TMEM lanes 32 (warp % 4) ..+31).
+// Two warps per SM sub-partition plus register prefetch (next tcgen05.ld / next gather issued before the
+// current chunk is converted) hide the TMEM, L2 and shared-memory latencies behind each other.
+#pragma once
+#include "gemm_tc.cuh"
+#include "pairs.cuh"
+
+namespace ciaosr {
+
+constexpr int HEAD_THREADS = 384;
+constexpr int NEPI = 256;
+
+// =====================================================================================================
+// pair kernel
+// =====================================================================================================
+struct PairParams {
+  PairConsts pc;
+  const float* coord; const float* cell;
+  const float* featT; const float* nlT;
+  int C, Cn, Dv, Dvp;
+  const float* Pk; const float* Pv; const float* G; int ldg;
+  const float* consts;        // 16 x 256 floats + bv5p[Dvp], see layout below
+  const uint8_t* blob; int units_per_tile; int units5;
+  float* x;                   // [total_q, Dvp]
+  long long total_rows; int n_tiles; int iters;     // iters = tiles per CTA (uniform over the grid)
+  float softmax_scale;
+};
+// consts layout (x256 floats): 0..3 rc_k, 4 b1_k, 5..7 b_k(layers 2..4), 8..11 rc_v, 12 b1_v, 13..15 b_v(2..4),
+//                               then bv5p[Dvp] (last value Linear bias, tap-major, zero padded)
+
+// layer 1 of imnet_k / imnet_v from the LR hoist:  relu(P[pix] + b1 + rc . [rel_y, rel_x, sc_y, sc_x])
+__device__ __forceinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
+                                           const float* __restrict__ P, const float* __restrict__ rc_s,
+                                           const float* __restrict__ b1_s) {
+  const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * 8 : nullptr;
+  float4 buf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) buf[j] = prow ? __ldg(prow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[4 * j] = buf[j].x; v[4 * j + 1] = buf[j].y; v[4 * j + 2] = buf[j].z; v[4 * j + 3] = buf[j].w; }
+    if (sl + 1 < 4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) buf[j] = prow ? __ldg(prow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int c0 = sl * 64 + half * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = c0 + i;
+      float t = v[i] + b1_s[c];
+      t = fmaf(rc_s[c], p.rel_y, t);
+      t = fmaf(rc_s[HID + c], p.rel_x, t);
+      t = fmaf(rc_s[2 * HID + c], p.sc_y, t);
+      t = fmaf(rc_s[3 * HID + c], p.sc_x, t);
+      v[i] = fmaxf(t, 0.0f);
+    }
+    slab_begin(s, e, sl, false);
+    a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
+    slab_done(s, sl);
+  }
+}
+
+template <int CL>
+__global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcShared s = tc_carve(smem);
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks5 = (P.units5 + 1) / 2;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  // tile of iteration i: clusters take CL consecutive tiles; every CTA runs `iters` iterations
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+
+  if (warp == 0) {
+    ProdState ps{0, 0, 0};
+    for (int it = 0; it < P.iters; ++it) produce_units<CL>(s, ps, P.blob, P.units_per_tile, cta_rank);
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0, 0};
+    for (int it = 0; it < P.iters; ++it) {
+      for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
+      for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0};
+    const float* cst = s.consts;
+    const float* bv5 = s.consts + 16 * HID;
+    const int C = P.C, H = P.pc.H, W = P.pc.W;
+    const bool tap32 = (C % 32) == 0;              // a 32-column chunk never straddles a tap
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      const long long R = tile * ROWS + row;
+      const bool valid = tile < P.n_tiles && R < P.total_rows;
+      PairInfo p;
+      if (valid) p = compute_pair(P.pc, P.coord, P.cell, R >> 2, (int)(R & 3));
+      else { p.pix = -1; p.gidx = -1; p.rel_y = p.rel_x = p.sc_y = p.sc_x = 0.0f; }
+
+      // ---- key chain -----------------------------------------------------------------------
+      gen_layer1(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
+      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 5 * HID);
+      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 6 * HID);
+      float logit = 0.0f;
+      {
+        const uint32_t d = epi_wait_d(s, e);
+        const float* bias_s = cst + 7 * HID;
+        const float4* grow = p.gidx >= 0 ? reinterpret_cast<const float4*>(P.G + (long long)p.gidx * P.ldg) + half * 8 : nullptr;
+        uint32_t buf[2][32];
+        float4 gb[8];
+        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gb[j] = grow ? __ldg(grow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          tmem_ld32_wait(buf[sl & 1]);
+          if (sl + 1 < 4) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
+          const int c0 = sl * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g = gb[j];
+            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j]) + bias_s[c0 + 4 * j], 0.0f), g.x, logit);
+            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 1]) + bias_s[c0 + 4 * j + 1], 0.0f), g.y, logit);
+            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 2]) + bias_s[c0 + 4 * j + 2], 0.0f), g.z, logit);
+            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 3]) + bias_s[c0 + 4 * j + 3], 0.0f), g.w, logit);
+          }
+          if (sl + 1 < 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gb[j] = grow ? __ldg(grow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (grow && half == 0) logit += __ldg(P.G + (long long)p.gidx * P.ldg + HID);
+        epi_release_d(s, e);
+      }
+      // combine the two column halves of every row, then softmax over the 4 neighbours (4 adjacent lanes)
+      float a;
+      {
+        s.xchg[half * ROWS + row] = logit;
+        epi_sync<NEPI>();
+        const float l = __fdiv_rn(s.xchg[row] + s.xchg[ROWS + row], P.softmax_scale);
+        float mx = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float ex = expf(l - mx);
+        float sum = ex + __shfl_xor_sync(0xffffffffu, ex, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        a = valid ? __fdiv_rn(ex, sum) : 0.0f;
+      }
+
+      // ---- value chain -----------------------------------------------------------------------
+      gen_layer1(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 13 * HID);
+      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 14 * HID);
+      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
+
+      // geometry of this row's latent code for the value gather
+      int py = 0, px = 0;
+      const float* fbase = nullptr;
+      const float* nbase = nullptr;
+      if (p.pix >= 0) {
+        const int hw = p.pix % (H * W);
+        py = hw / W; px = hw % W;
+        fbase = P.featT + (long long)p.pix * C;
+        if (P.nlT) nbase = P.nlT + (long long)p.pix * P.Cn;
+      }
+      // value[cp .. cp+3] in tap-major order (cp % 4 == 0); zeros outside the image / past Dv
+      auto value4 = [&](int cp) -> float4 {
+        if (fbase == nullptr || cp >= P.Dv) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cp >= 9 * C) return __ldg(reinterpret_cast<const float4*>(nbase + (cp - 9 * C)));
+        const int t = cp / C, ch = cp - t * C;
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return __ldg(reinterpret_cast<const float4*>(fbase + (dy * W + dx) * C + ch));
+      };
+      // 8 float4 = the 32 values of chunk [cp0, cp0+32)
+      auto load_values = [&](int cp0, float4 (&vb)[8]) {
+        if (tap32) {
+          const float* src = nullptr;
+          if (fbase != nullptr && cp0 < P.Dv) {
+            if (cp0 >= 9 * C) src = nbase + (cp0 - 9 * C);
+            else {
+              const int t = cp0 / C, ch = cp0 - t * C;
+              const int dy = t / 3 - 1, dx = t % 3 - 1;
+              if (py + dy >= 0 && py + dy < H && px + dx >= 0 && px + dx < W) src = fbase + (dy * W + dx) * C + ch;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            vb[g] = src ? __ldg(reinterpret_cast<const float4*>(src) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) vb[g] = value4(cp0 + 4 * g);
+        }
+      };
+      const long long q = R >> 2;
+      const int sub = (lane & 1) * 16 + ((lane >> 1) & 1) * 8;   // columns of a 32-chunk this lane ends up owning
+      for (int c = 0; c < nchunks5; ++c) {
+        const int units = min(2, P.units5 - 2 * c);
+        const int nsub = units * 2;                            // 32-column chunks per thread (alternating halves)
+        const uint32_t d = epi_wait_d(s, e);
+        uint32_t buf[2][32];
+        float4 vb[8];
+        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
+        load_values(c * 256 + half * 32, vb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k >= nsub) break;                                // nsub is 2 or 4, warp-uniform
+          const int cc = 2 * k + half;
+          const int cp0 = c * 256 + cc * 32;
+          float v[32];
+          tmem_ld32_wait(buf[k & 1]);
+          if (k + 1 < nsub) tmem_ld32_issue(lane_taddr + d * 256 + (cc + 2) * 32, buf[(k + 1) & 1]);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 val = vb[g];
+            const int o = cp0 + 4 * g;
+            v[4 * g] = a * val.x * (__uint_as_float(buf[k & 1][4 * g]) + bv5[o]);
+            v[4 * g + 1] = a * val.y * (__uint_as_float(buf[k & 1][4 * g + 1]) + bv5[o + 1]);
+            v[4 * g + 2] = a * val.z * (__uint_as_float(buf[k & 1][4 * g + 2]) + bv5[o + 2]);
+            v[4 * g + 3] = a * val.w * (__uint_as_float(buf[k & 1][4 * g + 3]) + bv5[o + 3]);
+          }
+          if (k + 1 < nsub) load_values(cp0 + 64, vb);
+          // sum over the 4 neighbour rows (lanes 4q..4q+3), leaving each lane with 8 of the 32 columns
+          float r16[16], r8[8];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float keep = (lane & 1) ? v[16 + i] : v[i];
+            const float send = (lane & 1) ? v[i] : v[16 + i];
+            r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float keep = (lane & 2) ? r16[8 + i] : r16[i];
+            const float send = (lane & 2) ? r16[i] : r16[8 + i];
+            r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(P.x + q * P.Dvp + cp0 + sub);
+            dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
+            dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
+          }
+        }
+        epi_release_d(s, e);
+      }
+    }
+  }
+  tc_teardown<CL>(tmem_base);
+}
+
+// =====================================================================================================
+// query kernel: imnet_q + residual
+// =====================================================================================================
+struct QueryParams {
+  const float* x; int Dvp;                 // [total_q, Dvp]
+  const float* consts;                     // x256 floats: 0..3 b_q(layers 1..4), 4..6 W5 rows, 7: b5 in [0..3)
+  const uint8_t* blob; int units_per_tile; int slabs1;
+  const float* lr; const float* coord; int H, W, Q;
+  float* out; long long total_q; int n_tiles; int iters;
+};
+
+template <int CL>
+__global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcShared s = tc_carve(smem);
+  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+
+  if (warp == 0) {
+    ProdState ps{0, 0, 0};
+    for (int it = 0; it < P.iters; ++it) produce_units<CL>(s, ps, P.blob, P.units_per_tile, cta_rank);
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0, 0};
+    for (int it = 0; it < P.iters; ++it) {
+      mma_job<CL>(s, tmem_base, m, P.slabs1, 2, true);
+      for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu};                     // A_free waits start at parity 1 (fresh barrier passes)
+    const float* cst = s.consts;
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      const long long g = tile * ROWS + row;
+      const bool valid = tile < P.n_tiles && g < P.total_q;
+      const float4* xrow = valid ? reinterpret_cast<const float4*>(P.x + g * P.Dvp) + half * 8 : nullptr;
+      // layer-1 operand: x (fp32) -> bf16 hi/lo slabs, streamed through the 4 slots
+      float4 xb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xb[j] = xrow ? __ldg(xrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int sl = 0; sl < P.slabs1; ++sl) {
+        const int slot = sl & 3;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[4 * j] = xb[j].x; v[4 * j + 1] = xb[j].y; v[4 * j + 2] = xb[j].z; v[4 * j + 3] = xb[j].w; }
+        if (sl + 1 < P.slabs1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xb[j] = xrow ? __ldg(xrow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        slab_begin(s, e, slot, true);
+        a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+        slab_done(s, slot);
+      }
+      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst);
+      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + HID);
+      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + 2 * HID);
+      // last hidden layer + the 256 -> 3 Linear on CUDA cores (each thread: its 32 columns of every slab)
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      {
+        const uint32_t d = epi_wait_d(s, e);
+        const float* bias_s = cst + 3 * HID;
+        uint32_t buf[2][32];
+        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          tmem_ld32_wait(buf[sl & 1]);
+          if (sl + 1 < 4) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
+          const int c0 = sl * 64 + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float h = fmaxf(__uint_as_float(buf[sl & 1][i]) + bias_s[c0 + i], 0.0f);
+            o0 = fmaf(h, cst[4 * HID + c0 + i], o0);
+            o1 = fmaf(h, cst[5 * HID + c0 + i], o1);
+            o2 = fmaf(h, cst[6 * HID + c0 + i], o2);
+          }
+        }
+        epi_release_d(s, e);
+      }
+      if (half == 1) { s.xchg[row * 3] = o0; s.xchg[row * 3 + 1] = o1; s.xchg[row * 3 + 2] = o2; }
+      epi_sync<NEPI>();
+      if (half == 0 && valid) {
+        o0 += s.xchg[row * 3] + cst[7 * HID];
+        o1 += s.xchg[row * 3 + 1] + cst[7 * HID + 1];
+        o2 += s.xchg[row * 3 + 2] + cst[7 * HID + 2];
+        if (P.lr) {
+          const int b = (int)(g / P.Q);
+          const float cy = P.coord[g * 2], cx = P.coord[g * 2 + 1];
+          const float* img = P.lr + (long long)b * 3 * P.H * P.W;
+          o0 += bilinear_border(img, P.H, P.W, cy, cx);
+          o1 += bilinear_border(img + P.H * P.W, P.H, P.W, cy, cx);
+          o2 += bilinear_border(img + 2 * P.H * P.W, P.H, P.W, cy, cx);
+        }
+        P.out[g * 3] = o0; P.out[g * 3 + 1] = o1; P.out[g * 3 + 2] = o2;
+      }
+      epi_sync<NEPI>();        // xchg is rewritten next tile
+    }
+  }
+  tc_teardown<CL>(tmem_base);
+}
+
+}  // namespace ciaosr
