@@ -39,17 +39,17 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
   const long long n_jobs = (long long)m_tiles * n_chunks;
 
   if (warp == 0) {
-    ProdState ps{0, 0, 0};
+    ProdState ps{0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
       const int units = min(2, g.nunits - 2 * nc);
       const long long image = ((long long)mt * ROWS) / g.rows_per_image;
       // blob order: for chunk: for slab: for unit
       const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES;
-      produce_units<1>(s, ps, src, g.kslabs * units, 0);
+      produce_job<1>(s, ps, src, g.kslabs, units, 0);
     }
   } else if (warp == 1) {
-    MmaState m{0, 0, 0, 0};
+    MmaState m{0, 0, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int nc = (int)(job % n_chunks);
       mma_job<1>(s, tmem_base, m, g.kslabs, min(2, g.nunits - 2 * nc), true);
@@ -57,7 +57,7 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
   } else if (warp >= 4) {
     const int row = threadIdx.x - EPI_T0;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0xFu};
+    EpiState e{0, 0xFu, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
       const int units = min(2, g.nunits - 2 * nc);
@@ -80,7 +80,7 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
         }
         slab_done(s, slot);
       }
-      const uint32_t d = epi_wait_d(s, e);
+      const uint32_t d = epi_wait_d(s, e, units);
 #pragma unroll 1
       for (int cc = 0; cc < units * 4; ++cc) {
         float v[32];
@@ -115,7 +115,7 @@ static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, co
 }
 
 // Pack a [N, K] operand into the unit blob: element (n, k) = src(n, k) (0 outside N x K).
-// Blob order: chunk (256 N) -> slab (64 K) -> unit (128 N); units past nunits are absent.
+// Blob order: chunk (256 N) -> slab (64 K) -> unit (128 N), each unit = [hi slab][lo slab].
 template <class Src>
 __global__ void tc_pack_operand_kernel(uint8_t* __restrict__ dst, int N, int K, int kslabs, int nunits,
                                        size_t image_stride, const Src src) {

@@ -63,7 +63,7 @@ __device__ __forceinline__ void gen_layer1(const TcShared& s, EpiState& e, int r
     }
     slab_begin(s, e, sl, false);
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    slab_done(s, sl);
+    if (sl & 1) slabs_done2(s, sl - 1, sl);
   }
 }
 
@@ -80,10 +80,18 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
 
   if (warp == 0) {
-    ProdState ps{0, 0, 0};
-    for (int it = 0; it < P.iters; ++it) produce_units<CL>(s, ps, P.blob, P.units_per_tile, cta_rank);
+    ProdState ps{0};
+    for (int it = 0; it < P.iters; ++it) {
+      const uint8_t* b = P.blob;
+      for (int j = 0; j < 6; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+      for (int c = 0; c < nchunks5; ++c) {
+        const int units = min(2, P.units5 - 2 * c);
+        produce_job<CL>(s, ps, b, 4, units, cta_rank);
+        b += (size_t)4 * units * UNIT_BYTES;
+      }
+    }
   } else if (warp == 1) {
-    MmaState m{0, 0, 0, 0};
+    MmaState m{0, 0, 0};
     for (int it = 0; it < P.iters; ++it) {
       for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
       for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
     const int half = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0};
+    EpiState e{0, 0, 0};
     const float* cst = s.consts;
     const float* bv5 = s.consts + 16 * HID;
     const int C = P.C, H = P.pc.H, W = P.pc.W;
@@ -109,9 +117,14 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
       gen_layer1(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 5 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 6 * HID);
+      // k.L4 is complete once both accumulator halves are; that also frees the operand slabs, so the value
+      // chain's layer 1 is built FIRST: the UMMAs of v.L2 then run while the logits are reduced from D.
+      const uint32_t dk = epi_wait_half(s, e, 0);
+      epi_wait_half(s, e, 1);
+      gen_layer1(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
       float logit = 0.0f;
       {
-        const uint32_t d = epi_wait_d(s, e);
+        const uint32_t d = dk;
         const float* bias_s = cst + 7 * HID;
         const float4* grow = p.gidx >= 0 ? reinterpret_cast<const float4*>(P.G + (long long)p.gidx * P.ldg) + half * 8 : nullptr;
         uint32_t buf[2][32];
@@ -154,8 +167,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
         a = valid ? __fdiv_rn(ex, sum) : 0.0f;
       }
 
-      // ---- value chain -----------------------------------------------------------------------
-      gen_layer1(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      // ---- value chain (layer 1 was built above) ----------------------------------------------------
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 13 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 14 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
@@ -204,10 +216,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
       for (int c = 0; c < nchunks5; ++c) {
         const int units = min(2, P.units5 - 2 * c);
         const int nsub = units * 2;                            // 32-column chunks per thread (alternating halves)
-        const uint32_t d = epi_wait_d(s, e);
+        uint32_t d = 0;
         uint32_t buf[2][32];
         float4 vb[8];
-        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
         load_values(c * 256 + half * 32, vb);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -215,8 +226,12 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
           const int cc = 2 * k + half;
           const int cp0 = c * 256 + cc * 32;
           float v[32];
+          if ((k & 1) == 0) {                                  // first chunk of an accumulator half
+            d = epi_wait_half(s, e, k >> 1);
+            tmem_ld32_issue(lane_taddr + d * 256 + cc * 32, buf[k & 1]);
+          }
           tmem_ld32_wait(buf[k & 1]);
-          if (k + 1 < nsub) tmem_ld32_issue(lane_taddr + d * 256 + (cc + 2) * 32, buf[(k + 1) & 1]);
+          if ((k & 1) == 0) tmem_ld32_issue(lane_taddr + d * 256 + (cc + 2) * 32, buf[(k + 1) & 1]);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 val = vb[g];
@@ -276,10 +291,15 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
 
   if (warp == 0) {
-    ProdState ps{0, 0, 0};
-    for (int it = 0; it < P.iters; ++it) produce_units<CL>(s, ps, P.blob, P.units_per_tile, cta_rank);
+    ProdState ps{0};
+    for (int it = 0; it < P.iters; ++it) {
+      const uint8_t* b = P.blob;
+      produce_job<CL>(s, ps, b, P.slabs1, 2, cta_rank);
+      b += (size_t)P.slabs1 * 2 * UNIT_BYTES;
+      for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+    }
   } else if (warp == 1) {
-    MmaState m{0, 0, 0, 0};
+    MmaState m{0, 0, 0};
     for (int it = 0; it < P.iters; ++it) {
       mma_job<CL>(s, tmem_base, m, P.slabs1, 2, true);
       for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
@@ -288,7 +308,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
     const int half = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0xFu};                     // A_free waits start at parity 1 (fresh barrier passes)
+    EpiState e{0, 0xFu, 0};                  // A_free waits start at parity 1 (fresh barrier passes)
     const float* cst = s.consts;
     for (int it = 0; it < P.iters; ++it) {
       const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
         }
         slab_begin(s, e, slot, true);
         a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
-        slab_done(s, slot);
+        if (sl & 1) slabs_done2(s, slot - 1, slot);            // slabs1 is even (Dvp % 128 == 0)
       }
       epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst);
       epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + HID);
@@ -319,14 +339,17 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
       // last hidden layer + the 256 -> 3 Linear on CUDA cores (each thread: its 32 columns of every slab)
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       {
-        const uint32_t d = epi_wait_d(s, e);
+        uint32_t d = 0;
         const float* bias_s = cst + 3 * HID;
         uint32_t buf[2][32];
-        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
+          if ((sl & 1) == 0) {
+            d = epi_wait_half(s, e, sl >> 1);
+            tmem_ld32_issue(lane_taddr + d * 256 + sl * 64 + half * 32, buf[sl & 1]);
+          }
           tmem_ld32_wait(buf[sl & 1]);
-          if (sl + 1 < 4) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
+          if ((sl & 1) == 0) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
           const int c0 = sl * 64 + half * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {

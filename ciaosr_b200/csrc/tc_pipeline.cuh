@@ -8,6 +8,9 @@
 // A "job" = D[j&1][:, 0:128*units) = A[128, 64*nslabs] . W[128*units, 64*nslabs]^T evaluated as three
 // bf16 UMMAs per product term (A_lo.W_hi + A_hi.W_hi on the hi slab, A_hi.W_lo on the lo slab).
 //
+// Both column halves of an accumulator are produced by the same N = 256 UMMAs; the D_READY[d][half]
+// pair is committed together at the end of the job.
+//
 // Template parameters:  CL   = CTAs per cluster sharing one weight stream (1 or 2).  With CL = 2 both
 //                              CTAs walk the same job sequence on different row tiles; CTA 0 loads every
 //                              hi slab, CTA 1 every lo slab, each copy is `.multicast::cluster` to both,
@@ -19,10 +22,10 @@
 // barrier      arrivals            producer -> consumer
 //   W_FULL[4]   1 + 16 KB tx        weight producer (bulk copy) -> UMMA issuer
 //   W_EMPTY[4]  CL (tcgen05.commit) UMMA issuer(s) -> weight producer
-//   A_READY[4]  NEPI row threads    operand writers -> UMMA issuer      (per slab slot)
+//   A_READY[4]  NEPI/32 row warps   operand writers -> UMMA issuer      (per slab slot)
 //   A_FREE[4]   1 (tcgen05.commit)  UMMA issuer -> operand writers      (only waited on when K > 256)
-//   D_READY[2]  1 (tcgen05.commit)  UMMA issuer -> row threads          (accumulator complete)
-//   D_FREE[2]   NEPI row threads    row threads -> UMMA issuer          (accumulator drained)
+//   D_READY[2][2] 1 (tcgen05.commit) UMMA issuer -> row threads         (one 128-column half of an accumulator complete)
+//   D_FREE[2]   NEPI/32 row warps   row threads -> UMMA issuer          (accumulator drained)
 #pragma once
 #include "tc_common.cuh"
 
@@ -38,7 +41,7 @@ constexpr int SM_CONST = SM_W + W_STAGES * SLAB_BYTES;  // floats: per-kernel co
 constexpr int CONST_FLOATS = 16 * HID + 2048;
 constexpr int SM_BAR = SM_CONST + CONST_FLOATS * 4;
 constexpr int BAR_W_FULL = 0, BAR_W_EMPTY = 4, BAR_A_READY = 8, BAR_A_FREE = 12, BAR_D_READY = 16,
-              BAR_D_FREE = 18, N_BARS = 20;
+              BAR_D_FREE = 20, N_BARS = 22;     // D_READY[d][n-half]: 16 + 2 d + nh
 constexpr int SM_SLOT = SM_BAR + N_BARS * 8;            // TMEM base address (4 B, padded to 16)
 constexpr int SM_XCHG = SM_SLOT + 16;                   // 1024 floats of row-thread exchange space
 constexpr int SM_TOTAL = SM_XCHG + 1024 * 4;
@@ -67,8 +70,9 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcShared& s, uint8_t* smem
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(bar_at(s, BAR_W_FULL + i), 1); mbar_init(bar_at(s, BAR_W_EMPTY + i), CL); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_at(s, BAR_A_READY + i), NEPI); mbar_init(bar_at(s, BAR_A_FREE + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_at(s, BAR_D_READY + i), 1); mbar_init(bar_at(s, BAR_D_FREE + i), NEPI); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_at(s, BAR_A_READY + i), NEPI / 32); mbar_init(bar_at(s, BAR_A_FREE + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_at(s, BAR_D_READY + i), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_at(s, BAR_D_FREE + i), NEPI / 32);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(smem) + SM_SLOT, 512);
@@ -87,108 +91,156 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
 }
 
 // ---- weight producer (warp 0; the whole warp walks the loop, lane 0 issues) -------------------------
-struct ProdState { int stage; uint32_t phase; uint32_t count; };
+// Ring protocol: one K-slab of a job occupies exactly one revolution of the 4-stage ring:
+//   stage 0 = W_hi rows   0..127, stage 1 = W_hi rows 128..255   (adjacent: one N = 256 B operand)
+//   stage 2 = W_lo rows   0..127, stage 3 = W_lo rows 128..255
+// Jobs with a single 128-column unit leave stages 1 and 3 empty (plain arrive, no bytes).
+struct ProdState { uint32_t phase; };
 
-// stream `nunits` consecutive weight units (hi slab, lo slab: 2 x 16 KB each) starting at `blob`
+// stream the weights of one job: units are stored (K-slab major) as [hi slab][lo slab] pairs
 template <int CL>
-__device__ __forceinline__ void produce_units(const TcShared& s, ProdState& ps, const uint8_t* blob, int nunits,
-                                              uint32_t cta_rank) {
+__device__ __forceinline__ void produce_job(const TcShared& s, ProdState& ps, const uint8_t* blob, int nslabs,
+                                            int units, uint32_t cta_rank) {
   const bool leader = (threadIdx.x & 31) == 0;
-  for (int i = 0; i < 2 * nunits; ++i) {
-    mbar_wait(bar_at(s, BAR_W_EMPTY + ps.stage), ps.phase ^ 1, 100);
-    if (leader) {
-      const uint32_t full = bar_at(s, BAR_W_FULL + ps.stage);
-      mbar_arrive_expect_tx(full, SLAB_BYTES);
-      const uint8_t* src = blob + (size_t)i * SLAB_BYTES;
-      const uint32_t dst = s.w + ps.stage * SLAB_BYTES;
-      if (CL == 1) bulk_g2s(dst, src, SLAB_BYTES, full);
-      else if ((ps.count & 1u) == cta_rank) bulk_g2s_mc(dst, src, SLAB_BYTES, full, (uint16_t)((1u << CL) - 1));
+  for (int sl = 0; sl < nslabs; ++sl) {
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      const int u = part & 1, lo = part >> 1;
+      mbar_wait(bar_at(s, BAR_W_EMPTY + part), ps.phase ^ 1, 100 + part);
+      if (leader) {
+        const uint32_t full = bar_at(s, BAR_W_FULL + part);
+        if (u < units) {
+          mbar_arrive_expect_tx(full, SLAB_BYTES);
+          const uint8_t* src = blob + ((size_t)(sl * units + u) * 2 + lo) * SLAB_BYTES;
+          const uint32_t dst = s.w + part * SLAB_BYTES;
+          if (CL == 1) bulk_g2s(dst, src, SLAB_BYTES, full);
+          else if ((uint32_t)u == cta_rank) bulk_g2s_mc(dst, src, SLAB_BYTES, full, (uint16_t)((1u << CL) - 1));
+        } else {
+          mbar_arrive(full);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    ++ps.count;
-    if (++ps.stage == W_STAGES) { ps.stage = 0; ps.phase ^= 1; }
+    ps.phase ^= 1;
   }
 }
 
 // ---- UMMA issuer (warp 1; the whole warp walks the loop, lane 0 issues and commits) -------------------
-struct MmaState { int stage; uint32_t wphase; uint32_t jobctr; uint32_t aready_bits; };
+struct MmaState { uint32_t wphase; uint32_t jobctr; uint32_t aready_bits; };
 
-template <int CL>
-__device__ __forceinline__ void release_stage(const TcShared& s, MmaState& m, bool leader) {
-  if (leader) {
-    if (CL == 1) umma_commit(bar_at(s, BAR_W_EMPTY + m.stage));
-    else umma_commit_mc(bar_at(s, BAR_W_EMPTY + m.stage), (uint16_t)((1u << CL) - 1));
-  }
-  __syncwarp();
-  if (++m.stage == W_STAGES) { m.stage = 0; m.wphase ^= 1; }
+// descriptor for a slab at smem address `addr` (+ k-step offset): only the low word varies
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+      : "memory");
 }
 
-// one job: D[jobctr & 1][:, 0 : 128*units) = A (nslabs x 64 K) * W^T ; A slabs cycle through the 4 smem slots
+template <int CL>
+__device__ __forceinline__ void release_stage(const TcShared& s, int stage) {
+  if (CL == 1) umma_commit(bar_at(s, BAR_W_EMPTY + stage));
+  else umma_commit_mc(bar_at(s, BAR_W_EMPTY + stage), (uint16_t)((1u << CL) - 1));
+}
+
+// one job: D[jobctr & 1][:, 0 : 128*units) = A (nslabs x 64 K) * W^T ; A slabs cycle through the 4 smem slots.
+// One UMMA covers all 128*units columns (N = 256 for full jobs): 12 instructions per K-slab, each worth
+// 128 tensor-core cycles, so the single issuing thread is never the bottleneck.
 template <int CL>
 __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, MmaState& m, int nslabs,
                                         int units, bool a_new) {
-  constexpr uint32_t IDESC = make_idesc_bf16(ROWS, UNIT_N);
   const bool leader = (threadIdx.x & 31) == 0;
+  const uint32_t idesc = make_idesc_bf16(ROWS, UNIT_N * units);
   const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
   mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
   tc_fence_after();
+  const uint32_t dcol = tmem_base + d * 256;
+  const uint32_t b_hi = desc_lo(s.w), b_lo = desc_lo(s.w + 2 * SLAB_BYTES);
   for (int sl = 0; sl < nslabs; ++sl) {
     const int slot = sl & 3;
     if (a_new) {
       mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
       m.aready_bits ^= 1u << slot;
-      tc_fence_after();
     }
-    const uint32_t a_hi = s.a_hi + slot * SLAB_BYTES, a_lo = s.a_lo + slot * SLAB_BYTES;
-    for (int u = 0; u < units; ++u) {
-      const uint32_t dcol = tmem_base + d * 256 + u * UNIT_N;
-      // hi slab of the unit: A_lo.W_hi (small term first) and A_hi.W_hi
-      mbar_wait(bar_at(s, BAR_W_FULL + m.stage), m.wphase, 220);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t w_hi = s.w + m.stage * SLAB_BYTES;
+    const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
+    // W_hi (stages 0,1): A_lo.W_hi (small term first) and A_hi.W_hi
+    mbar_wait(bar_at(s, BAR_W_FULL + 0), m.wphase, 220);
+    mbar_wait(bar_at(s, BAR_W_FULL + 1), m.wphase, 221);
+    tc_fence_after();
+    if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t bh = make_desc_sw128(w_hi + ks * 32);
-          umma_bf16(dcol, make_desc_sw128(a_lo + ks * 32), bh, IDESC, (sl | ks) != 0 ? 1u : 0u);
-          umma_bf16(dcol, make_desc_sw128(a_hi + ks * 32), bh, IDESC, 1u);
-        }
+      for (int ks = 0; ks < 4; ++ks) {
+        umma_lo(dcol, a_lo + 2 * ks, b_hi + 2 * ks, idesc, (sl | ks) != 0 ? 1u : 0u);
+        umma_lo(dcol, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
       }
-      release_stage<CL>(s, m, leader);
-      // lo slab: A_hi.W_lo
-      mbar_wait(bar_at(s, BAR_W_FULL + m.stage), m.wphase, 221);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t w_lo = s.w + m.stage * SLAB_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(dcol, make_desc_sw128(a_hi + ks * 32), make_desc_sw128(w_lo + ks * 32), IDESC, 1u);
-      }
-      release_stage<CL>(s, m, leader);
+      release_stage<CL>(s, 0);
+      release_stage<CL>(s, 1);
     }
-    if (leader) umma_commit(bar_at(s, BAR_A_FREE + slot));
     __syncwarp();
+    // W_lo (stages 2,3): A_hi.W_lo
+    mbar_wait(bar_at(s, BAR_W_FULL + 2), m.wphase, 222);
+    mbar_wait(bar_at(s, BAR_W_FULL + 3), m.wphase, 223);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) umma_lo(dcol, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+      release_stage<CL>(s, 2);
+      release_stage<CL>(s, 3);
+      umma_commit(bar_at(s, BAR_A_FREE + slot));
+    }
+    __syncwarp();
+    m.wphase ^= 1;
   }
-  if (leader) umma_commit(bar_at(s, BAR_D_READY + d));
+  if (leader) {
+    umma_commit(bar_at(s, BAR_D_READY + 2 * d));
+    if (units == 2) umma_commit(bar_at(s, BAR_D_READY + 2 * d + 1));   // waited on only by 2-unit jobs
+  }
   __syncwarp();
   ++m.jobctr;
 }
 
 // ---- row-thread helpers --------------------------------------------------------------------------------
-struct EpiState { uint32_t jobctr; uint32_t afree_bits; };   // afree_bits: parity to wait on next, per slot
+// afree_bits / dready_bits: parity to wait on next, per operand slot / per (accumulator, column half)
+struct EpiState { uint32_t jobctr; uint32_t afree_bits; uint32_t dready_bits; };
 
 __device__ __forceinline__ void slab_begin(const TcShared& s, EpiState& e, int slot, bool wait_free) {
   if (wait_free) mbar_wait(bar_at(s, BAR_A_FREE + slot), (e.afree_bits >> slot) & 1, 300 + slot);
   e.afree_bits ^= 1u << slot;
 }
+// Publish operand slabs to the UMMA issuer.  Every writer thread makes its own st.shared visible to
+// the async proxy (fence.proxy.async, ONE per call: it drains the thread's outstanding shared stores
+// and is the most expensive instruction of the epilogue), the warp converges, and one lane arrives
+// (A_READY counts warps, not threads: same-address mbarrier arrivals serialise).
 __device__ __forceinline__ void slab_done(const TcShared& s, int slot) {
   fence_proxy_async();
-  mbar_arrive(bar_at(s, BAR_A_READY + slot));
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar_at(s, BAR_A_READY + slot));
 }
-__device__ __forceinline__ uint32_t epi_wait_d(const TcShared& s, EpiState& e) {
-  const uint32_t d = e.jobctr & 1, n = e.jobctr >> 1;
-  mbar_wait(bar_at(s, BAR_D_READY + d), n & 1, 310);
+__device__ __forceinline__ void slabs_done2(const TcShared& s, int slot_a, int slot_b) {
+  fence_proxy_async();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    mbar_arrive(bar_at(s, BAR_A_READY + slot_a));
+    mbar_arrive(bar_at(s, BAR_A_READY + slot_b));
+  }
+}
+// wait until column half `nh` of the current job's accumulator is complete; returns the accumulator index
+__device__ __forceinline__ uint32_t epi_wait_half(const TcShared& s, EpiState& e, int nh) {
+  const uint32_t d = e.jobctr & 1, b = 2 * d + nh;
+  mbar_wait(bar_at(s, BAR_D_READY + b), (e.dready_bits >> b) & 1, 310 + b);
+  e.dready_bits ^= 1u << b;
   tc_fence_after();
+  return d;
+}
+__device__ __forceinline__ uint32_t epi_wait_d(const TcShared& s, EpiState& e, int units) {
+  uint32_t d = 0;
+  for (int nh = 0; nh < units; ++nh) d = epi_wait_half(s, e, nh);
   return d;
 }
 // barrier among the NEPI row threads only (named barrier 1)
@@ -198,32 +250,44 @@ __device__ __forceinline__ void epi_sync() {
 }
 __device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
   tc_fence_before();
-  mbar_arrive(bar_at(s, BAR_D_FREE + (e.jobctr & 1)));
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar_at(s, BAR_D_FREE + (e.jobctr & 1)));
   ++e.jobctr;
 }
 
 // Hidden-layer epilogue: next A = relu(D + bias).  HALVES = 1: this thread converts all 64 columns of
-// every slab; HALVES = 2: only columns [32*half, 32*half + 32).  The TMEM load of the next slab is in
-// flight while the current one is converted and stored.
+// every slab; HALVES = 2: only columns [32*half, 32*half + 32).  Columns 0..127 are converted as soon as
+// the first accumulator half is complete (the UMMAs of the second half are still running).
 template <bool WAIT_FREE, int HALVES>
 __device__ __forceinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t lane_taddr, int row, int half,
                                            const float* __restrict__ bias_s) {
-  const uint32_t d = epi_wait_d(s, e);
   constexpr int NCH = 4 * (2 / HALVES);          // 32-column chunks this thread handles
+  constexpr int PER_HALF = NCH / 2;
   uint32_t buf[2][32];
   auto col_of = [&](int c) { return HALVES == 2 ? (c * 64 + half * 32) : (c * 32); };
-  tmem_ld32_issue(lane_taddr + d * 256 + col_of(0), buf[0]);
+  uint32_t d = 0;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    if (c % PER_HALF == 0) {                     // first chunk of an accumulator half
+      d = epi_wait_half(s, e, c / PER_HALF);
+      tmem_ld32_issue(lane_taddr + d * 256 + col_of(c), buf[c & 1]);
+    }
     tmem_ld32_wait(buf[c & 1]);
-    if (c + 1 < NCH) tmem_ld32_issue(lane_taddr + d * 256 + col_of(c + 1), buf[(c + 1) & 1]);
+    if ((c + 1) % PER_HALF != 0) tmem_ld32_issue(lane_taddr + d * 256 + col_of(c + 1), buf[(c + 1) & 1]);
     const int col = col_of(c), sl = col >> 6;
     if (HALVES == 2 || (c & 1) == 0) slab_begin(s, e, sl, WAIT_FREE);
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(__uint_as_float(buf[c & 1][i]) + bias_s[col + i], 0.0f);
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = reinterpret_cast<const float4*>(bias_s + col)[j];
+      v[4 * j] = fmaxf(__uint_as_float(buf[c & 1][4 * j]) + b4.x, 0.0f);
+      v[4 * j + 1] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 1]) + b4.y, 0.0f);
+      v[4 * j + 2] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 2]) + b4.z, 0.0f);
+      v[4 * j + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 3]) + b4.w, 0.0f);
+    }
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
-    if (HALVES == 2 || (c & 1) == 1) slab_done(s, sl);
+    if (HALVES == 2) { if (c & 1) slabs_done2(s, sl - 1, sl); }      // one proxy fence per accumulator half
+    else if (c & 1) slab_done(s, sl);
   }
   epi_release_d(s, e);
 }
