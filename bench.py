@@ -202,6 +202,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="replay the generator forward as a CUDA graph")
+    ap.add_argument("--channels-last", type=int, default=1, help="PyTorch encoder in channels_last")
+    ap.add_argument("--encoder-tf32", type=int, default=0,
+                    help="allow TF32 cuDNN convolutions in the PyTorch encoder (PyTorch's default is 1; 0 keeps the "
+                         "encoder fp32 so that end-to-end outputs match the fp32 reference)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,8 +224,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(args.encoder_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
     model = build_model(args.engine).to(dev)
     gen = model.generator
+    if args.channels_last:
+        gen.to(memory_format=torch.channels_last)
+    gen.channels_last = bool(args.channels_last)
+    gen.cuda_graph = bool(args.cuda_graph)
     lq_h, coord_h, cell_h = make_inputs(B, 100 + rank)
     lq_h, coord_h, cell_h = lq_h.pin_memory(), coord_h.pin_memory(), cell_h.pin_memory()
     lq_d = ((lq_h - torch.tensor(RGB_MEAN).view(1, 3, 1, 1))).to(dev)     # normalised, as forward_test passes it
@@ -280,18 +292,29 @@ def main():
     torch.cuda.synchronize()
     log("warm-up done")
     with ClockSampler(local) as clk:
-        ms_step, launches, stages = timed(step_device, args.steps, profile=True)
+        ms_step, launches, _ = timed(step_device, args.steps)
     clocks = clk.summary()
-    log(f"timed region done: {ms_step:.1f} ms/step")
+    log(f"timed region done: {ms_step:.2f} ms/step")
+    # stage timing needs the library's host code to run (it records CUDA events around its stages), so it
+    # is taken in eager mode right after; the same kernels run when the step is replayed from a graph
+    graphed = gen.cuda_graph
+    gen.cuda_graph = False
+    for _ in range(2):
+        step_device()
+    ms_eager, launches_eager, stages = timed(step_device, args.steps, profile=True)
+    if graphed:
+        launches = launches_eager             # a replayed graph launches the same kernels
     # head alone (feature resident): what the roofline explains
     with torch.no_grad():
-        feat = gen.gen_feature(lq_d)
+        feat = gen.gen_feature(lq_d.contiguous(memory_format=torch.channels_last) if args.channels_last else lq_d)
+        feat = [f.contiguous() for f in feat]
     ms_head, _, _ = timed(lambda: gen.query_rgb(feat, coord_d, cell_d, lr_image=lq_d, eval_bsize=EVAL_BSIZE), args.steps)
-    ms_enc, _, _ = timed(lambda: gen.gen_feature(lq_d), args.steps)
+    gen.cuda_graph = graphed
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
-    log(f"head {ms_head:.1f} ms, encoder {ms_enc:.1f} ms, e2e {ms_e2e:.1f} ms")
+    ms_enc = ms_eager - ms_head
+    log(f"eager step {ms_eager:.2f} ms, head {ms_head:.2f} ms, e2e {ms_e2e:.2f} ms")
 
     if rank == 0:
         from oracle.ciaosr_oracle import cross_scale_flops, head_flops_per_query
@@ -320,8 +343,10 @@ def main():
                        "px_per_step_per_gpu": npx, "eval_bsize": EVAL_BSIZE, "engine": engine,
                        "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB",
                        "head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
-                       "head_ms": ms_head, "encoder_ms": ms_enc,
-                       "encoder": "PyTorch RDN fp32 (cudnn.allow_tf32=%s)" % torch.backends.cudnn.allow_tf32},
+                       "head_ms": ms_head, "eager_step_ms": ms_eager, "encoder_ms_est": ms_enc,
+                       "encoder": "PyTorch RDN fp32 (cudnn.allow_tf32=%s, channels_last=%s)"
+                                  % (torch.backends.cudnn.allow_tf32, bool(args.channels_last)),
+                       "cuda_graph": bool(args.cuda_graph)},
             "clocks": clocks,
             "e2e": {"value": world * npx / (ms_e2e * 1e-3) / 1e6, "unit": "Mpix/s",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},

@@ -20,7 +20,8 @@ ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
 
 E_INVALID, E_WORKSPACE, E_CUDA, E_NO_DEVICE = -1, -2, -3, -4
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libciaosr_b200.so")
+LIB_PATH = os.environ.get(
+    "CIAOSR_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libciaosr_b200.so"))
 
 # every symbol include/ciaosr_b200.h declares
 EXPORTS = (

@@ -34,7 +34,7 @@ struct PairParams {
 //                               then bv5p[Dvp] (last value Linear bias, tap-major, zero padded)
 
 // layer 1 of imnet_k / imnet_v from the LR hoist:  relu(P[pix] + b1 + rc . [rel_y, rel_x, sc_y, sc_x])
-__device__ __forceinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
+__device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
                                            const float* __restrict__ P, const float* __restrict__ rc_s,
                                            const float* __restrict__ b1_s) {
   const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * 8 : nullptr;
@@ -81,20 +81,32 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
 
   if (warp == 0) {
     ProdState ps{0};
+#ifdef CIAOSR_TC_QUARTER
+    uint32_t stage = 0;
+#define PAIR_PRODUCE(b, ns, un) produce_job_q<CL>(s, ps, stage, b, ns, un, cta_rank)
+#else
+#define PAIR_PRODUCE(b, ns, un) produce_job<CL>(s, ps, b, ns, un, cta_rank)
+#endif
     for (int it = 0; it < P.iters; ++it) {
       const uint8_t* b = P.blob;
-      for (int j = 0; j < 6; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+      for (int j = 0; j < 6; ++j) { PAIR_PRODUCE(b, 4, 2); b += (size_t)8 * UNIT_BYTES; }
       for (int c = 0; c < nchunks5; ++c) {
         const int units = min(2, P.units5 - 2 * c);
-        produce_job<CL>(s, ps, b, 4, units, cta_rank);
+        PAIR_PRODUCE(b, 4, units);
         b += (size_t)4 * units * UNIT_BYTES;
       }
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
+#ifdef CIAOSR_TC_QUARTER
+    uint32_t stage = 0;
+#define PAIR_MMA(ns, un, an) mma_job_q<CL>(s, tmem_base, m, stage, ns, un, an)
+#else
+#define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an)
+#endif
     for (int it = 0; it < P.iters; ++it) {
-      for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
-      for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+      for (int j = 0; j < 6; ++j) PAIR_MMA(4, 2, true);
+      for (int c = 0; c < nchunks5; ++c) PAIR_MMA(4, min(2, P.units5 - 2 * c), c == 0);
     }
   } else if (warp >= 4) {
     const int half = (warp - 4) >> 2;

@@ -32,7 +32,7 @@ class LocalImplicitSRNet(nn.Module):
                  non_local_attn=True, multi_scale=[2], softmax_scale=1,
                  # keywords the 002 configs pass (configs/002_real_wogan...py:54-59)
                  local_ensemble_coord=True, imnet_k_type=None, imnet_v_type=None, res=True,
-                 cat_nla_v=None, engine="auto"):
+                 cat_nla_v=None, engine="auto", cuda_graph=False, channels_last=True):
         super().__init__()
         self.feat_unfold = feat_unfold
         self.eval_bsize = eval_bsize
@@ -42,6 +42,12 @@ class LocalImplicitSRNet(nn.Module):
         self.softmax_scale = softmax_scale
         self.res = res
         self.engine = engine
+        # plumbing knobs (no effect on results): replay the whole inference forward as one CUDA graph per
+        # input shape (the PyTorch encoder is ~450 small launches and is CPU-launch-bound otherwise), and
+        # run the encoder convolutions in channels_last (cuDNN's native layout; saves the NCHW<->NHWC passes)
+        self.cuda_graph = cuda_graph
+        self.channels_last = channels_last
+        self._graphs = {}
         if not local_ensemble_coord:
             raise NotImplementedError("local_ensemble_coord=False has no counterpart in the reference head")
 
@@ -95,10 +101,46 @@ class LocalImplicitSRNet(nn.Module):
                 "ciaosr_b200 implements the inference forward of the head only; run training "
                 "forwards under torch.no_grad() or with test_mode=True (SURVEY.md 8f #4)")
         with torch.no_grad():
-            feature = self.gen_feature(x)
-            chunk = self.eval_bsize if (self.eval_bsize is not None and test_mode) else None
-            return self.query_rgb(feature, coord, cell, lr_image=x if self.res else None,
-                                  eval_bsize=chunk)
+            if self.cuda_graph and x.is_cuda:
+                return self._forward_graphed(x, coord, cell, test_mode)
+            return self._forward_eager(x, coord, cell, test_mode)
+
+    def _forward_eager(self, x, coord, cell, test_mode):
+        xin = x.contiguous(memory_format=torch.channels_last) if (self.channels_last and x.is_cuda) else x
+        feature = [f.contiguous() for f in self.gen_feature(xin)]
+        chunk = self.eval_bsize if (self.eval_bsize is not None and test_mode) else None
+        return self.query_rgb(feature, coord, cell, lr_image=x.contiguous() if self.res else None,
+                              eval_bsize=chunk)
+
+    def _forward_graphed(self, x, coord, cell, test_mode):
+        """One CUDA graph per (shapes, test_mode); inputs are copied into static buffers and the
+        static output is cloned, so callers see ordinary tensors."""
+        # head weights are packed into the plan: a new graph is needed when any of them changes
+        sig = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
+                    if n.startswith(("imnet_", "cs_attn.")))
+        key = (tuple(x.shape), tuple(coord.shape), bool(test_mode), x.device.index, sig)
+        entry = self._graphs.get(key)
+        if entry is None:
+            sx, sc, sl = x.clone(), coord.clone(), cell.clone()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):                      # warm-up: plan, workspace, cuDNN algos
+                for _ in range(2):
+                    self._forward_eager(sx, sc, sl, test_mode)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                so = self._forward_eager(sx, sc, sl, test_mode)
+            entry = (graph, sx, sc, sl, so)
+            if len(self._graphs) >= 8:                         # bound the pools kept alive
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = entry
+        graph, sx, sc, sl, so = entry
+        sx.copy_(x, non_blocking=True)
+        sc.copy_(coord, non_blocking=True)
+        sl.copy_(cell, non_blocking=True)
+        graph.replay()
+        return so.clone()
 
     def query_rgb(self, features, coord, scale=None, lr_image=None, eval_bsize=None):
         """ciaosr_net.py:113-224 (`scale` is the reference's name for the cell tensor)."""
