@@ -60,7 +60,13 @@ def fill_module(module, seed=0):
         for k, v in sd.items():
             if not torch.is_floating_point(v):
                 continue
-            t = synth_tensor(k, v.shape, seed, gain=0.35 if k in small else 1.4)
+            if k in small:
+                gain = 0.35
+            elif k.startswith(("imnet_", "cs_attn.")) or ".imnet_" in k or ".cs_attn." in k:
+                gain = 1.4
+            else:
+                gain = 0.8        # encoder convolutions: keeps the 130-conv RDN's features O(1)
+            t = synth_tensor(k, v.shape, seed, gain=gain)
             if t is not None:
                 v.copy_(t.to(v.dtype))
     return module
