@@ -12,8 +12,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_lon
 ABI_VERSION = 1
 MAX_LAYERS = 8
 MAX_SCALES = 4
-N_STAGES = 5
-STAGE_NAMES = ("layout", "cross_scale_attn", "lr_precompute", "pair_mlp", "query_mlp")
+N_STAGES = 6
+STAGE_NAMES = ("layout", "cross_scale_attn", "lr_precompute", "pair_mlp", "query_mlp", "rdn_encoder")
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
@@ -30,6 +30,7 @@ EXPORTS = (
     "ciaosr_plan_bytes", "ciaosr_plan_init", "ciaosr_workspace_bytes",
     "ciaosr_cross_scale_attn_workspace_bytes", "ciaosr_cross_scale_attn_forward", "ciaosr_query_rgb_forward",
     "ciaosr_tile_blend_accumulate", "ciaosr_tile_blend_finish",
+    "ciaosr_rdn_plan_bytes", "ciaosr_rdn_plan_init", "ciaosr_rdn_workspace_bytes", "ciaosr_rdn_forward",
 )
 
 
@@ -54,6 +55,15 @@ class HeadDesc(Structure):
                 ("local_size", c_int32), ("non_local_attn", c_int32), ("softmax_scale", c_float),
                 ("imnet_q", MlpDesc), ("imnet_k", MlpDesc), ("imnet_v", MlpDesc),
                 ("cs_attn", CsAttnDesc)]
+
+
+class RdnDesc(Structure):
+    _fields_ = [("abi_version", c_int32), ("mid_channels", c_int32), ("channel_growth", c_int32),
+                ("num_blocks", c_int32), ("num_layers", c_int32),
+                ("sfe1_w", c_void_p), ("sfe1_b", c_void_p), ("sfe2_w", c_void_p), ("sfe2_b", c_void_p),
+                ("dense_w", POINTER(c_void_p)), ("dense_b", POINTER(c_void_p)),
+                ("lff_w", POINTER(c_void_p)), ("lff_b", POINTER(c_void_p)),
+                ("gff0_w", c_void_p), ("gff0_b", c_void_p), ("gff1_w", c_void_p), ("gff1_b", c_void_p)]
 
 
 class CiaoSRNativeError(RuntimeError):
@@ -108,6 +118,11 @@ def load():
         c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.ciaosr_tile_blend_finish.argtypes = [
         c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.ciaosr_rdn_plan_bytes.argtypes = [POINTER(RdnDesc), POINTER(c_size_t)]
+    lib.ciaosr_rdn_plan_init.argtypes = [POINTER(RdnDesc), c_void_p, c_size_t, c_void_p]
+    lib.ciaosr_rdn_workspace_bytes.argtypes = [POINTER(RdnDesc), c_int, c_int, c_int, POINTER(c_size_t)]
+    lib.ciaosr_rdn_forward.argtypes = [POINTER(RdnDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]
     for name in EXPORTS[3:]:  # everything after the three non-int getters
         getattr(lib, name).restype = c_int
     if lib.ciaosr_abi_version() != ABI_VERSION:

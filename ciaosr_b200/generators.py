@@ -177,9 +177,32 @@ class LocalImplicitSRRDN(LocalImplicitSRNet):
         self.rdbs = self.encoder.rdbs
         self.gff = self.encoder.gff
         self.num_blocks = self.encoder.num_blocks
+        self._enc_geom = (self.encoder.mid_channels, self.encoder.channel_growth, self.encoder.num_blocks,
+                          self.encoder.num_layers)
         del self.encoder
+        # encoder fast path: the same RDN on the tensor cores with fp32-grade accuracy.
+        # 'auto' uses it for CUDA inputs when the geometry admits it (mid_channels == growth == 64);
+        # False keeps the PyTorch / cuDNN encoder of the reference.
+        self.native_encoder = "auto"
+        self._enc_plan = None
+        self._enc_key = None
+
+    def _native_encoder_plan(self):
+        names = ("sfe1.", "sfe2.", "rdbs.", "gff.")
+        params = {k: v for k, v in self.state_dict().items() if k.startswith(names)}
+        key = tuple((k, v.data_ptr(), v._version) for k, v in params.items())
+        if self._enc_plan is None or key != self._enc_key:
+            mid, growth, nb, nl = self._enc_geom
+            self._enc_plan = native.RdnPlan(params, mid, growth, nb, nl)
+            self._enc_key = key
+        return self._enc_plan
 
     def gen_feature(self, x):
+        mid, growth = self._enc_geom[:2]
+        if self.native_encoder and x.is_cuda and mid == 64 and growth == 64 and not torch.is_grad_enabled():
+            return [self._native_encoder_plan().forward(x)]
+        if self.native_encoder is True:
+            raise RuntimeError("native_encoder=True needs a CUDA input, no_grad, and mid_channels == growth == 64")
         sfe1 = self.sfe1(x)
         x = self.sfe2(sfe1)
         local_features = []

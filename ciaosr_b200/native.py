@@ -234,3 +234,64 @@ class CsAttnOnlyPlan(HeadPlan):
             full[f"{name}.layers.2.weight"], full[f"{name}.layers.2.bias"] = zeros(dout, 1), zeros(dout)
         super().__init__(full, channels, local_size=2, non_local_attn=True, multi_scale=multi_scale,
                          softmax_scale=1.0, cs_softmax_scale=cs_softmax_scale)
+
+
+class RdnPlan:
+    """Native RDN encoder (ciaosr_rdn_* in the C ABI): weights packed once, forward on the
+    tensor cores with fp32-grade accuracy.  `params`: the generator's hoisted encoder
+    state (sfe1.*, sfe2.*, rdbs.N.layers.M.conv.*, rdbs.N.lff.*, gff.0.*, gff.1.*)."""
+
+    def __init__(self, params, mid_channels, channel_growth, num_blocks, num_layers):
+        lib = _lib.load()
+        self._keep = []
+        self.device = params["sfe1.weight"].device
+        if self.device.type != "cuda":
+            raise RuntimeError("RdnPlan needs CUDA parameters")
+
+        def p(key):
+            t = _f32c(params[key].detach(), key)
+            self._keep.append(t)
+            return t.data_ptr()
+
+        d = _lib.RdnDesc()
+        d.abi_version = _lib.ABI_VERSION
+        d.mid_channels, d.channel_growth = int(mid_channels), int(channel_growth)
+        d.num_blocks, d.num_layers = int(num_blocks), int(num_layers)
+        d.sfe1_w, d.sfe1_b, d.sfe2_w, d.sfe2_b = p("sfe1.weight"), p("sfe1.bias"), p("sfe2.weight"), p("sfe2.bias")
+        n = num_blocks * num_layers
+        self._dw = (ctypes.c_void_p * n)(*[p(f"rdbs.{r}.layers.{l}.conv.weight")
+                                           for r in range(num_blocks) for l in range(num_layers)])
+        self._db = (ctypes.c_void_p * n)(*[p(f"rdbs.{r}.layers.{l}.conv.bias")
+                                           for r in range(num_blocks) for l in range(num_layers)])
+        self._lw = (ctypes.c_void_p * num_blocks)(*[p(f"rdbs.{r}.lff.weight") for r in range(num_blocks)])
+        self._lb = (ctypes.c_void_p * num_blocks)(*[p(f"rdbs.{r}.lff.bias") for r in range(num_blocks)])
+        d.dense_w, d.dense_b = self._dw, self._db
+        d.lff_w, d.lff_b = self._lw, self._lb
+        d.gff0_w, d.gff0_b, d.gff1_w, d.gff1_b = p("gff.0.weight"), p("gff.0.bias"), p("gff.1.weight"), p("gff.1.bias")
+        self.desc = d
+        self.channels = int(mid_channels)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.ciaosr_rdn_plan_bytes(ctypes.byref(d), ctypes.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.buf = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.ciaosr_rdn_plan_init(ctypes.byref(d), _ptr(self.buf), nbytes.value,
+                                                _stream(self.device)))
+        self._ws = None
+
+    def forward(self, x):
+        """x [B,3,H,W] -> feature [B,64,H,W]."""
+        x = _f32c(x, "x")
+        B, c, H, W = x.shape
+        if c != 3:
+            raise ValueError(f"RDN expects 3 input channels, got {c}")
+        n = ctypes.c_size_t(0)
+        _lib.check(_lib.load().ciaosr_rdn_workspace_bytes(ctypes.byref(self.desc), B, H, W, ctypes.byref(n)))
+        if self._ws is None or self._ws.numel() < n.value:
+            self._ws = None
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        out = torch.empty(B, self.channels, H, W, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ciaosr_rdn_forward(ctypes.byref(self.desc), _ptr(self.buf), _ptr(x), B, H, W,
+                                                      _ptr(out), _ptr(self._ws), self._ws.numel(),
+                                                      _stream(self.device)))
+        return out

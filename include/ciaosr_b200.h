@@ -123,8 +123,9 @@ int ciaosr_engine_supported(const ciaosr_head_desc* desc, int engine);
  * caller's stream.  ciaosr_profile_read synchronises those events, adds the
  * elapsed milliseconds per stage into ms[0..n) / launches[0..n) and clears the
  * list.  Stages: 0 layout, 1 cross-scale attention, 2 LR precompute,
- * 3 (query,neighbour) MLP stacks + inner attention, 4 query MLP + residual. */
-#define CIAOSR_N_STAGES 5
+ * 3 (query,neighbour) MLP stacks + inner attention, 4 query MLP + residual,
+ * 5 native RDN encoder. */
+#define CIAOSR_N_STAGES 6
 int ciaosr_profile_enable(int on);
 int ciaosr_profile_read(float* ms, int* launches, int n);
 
@@ -169,6 +170,32 @@ int ciaosr_query_rgb_forward(const ciaosr_head_desc* desc, const void* plan,
                              int B, int H, int W, int q, int eval_bsize,
                              int engine, float* out,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- RDN encoder fast path (SURVEY.md 8f "next" #2) ------------------------------
+ * mmedit's RDN as the generator hoists it (ciaosr_net.py:314-318) and runs it in
+ * gen_feature (ciaosr_net.py:321-342): sfe1, sfe2, num_blocks x [num_layers x
+ * (conv3x3 + ReLU, dense concat), 1x1 local fusion, + input], 1x1 + 3x3 global fusion,
+ * + sfe1 output.  Weights are [out, in, kh, kw] row-major as in the state_dict;
+ * dense_w/dense_b are HOST arrays of num_blocks*num_layers device pointers
+ * (block-major), lff_w/lff_b host arrays of num_blocks device pointers.
+ * Only mid_channels == channel_growth == 64 is implemented. */
+typedef struct ciaosr_rdn_desc {
+  int32_t abi_version;
+  int32_t mid_channels, channel_growth, num_blocks, num_layers;
+  const float* sfe1_w; const float* sfe1_b;     /* [64,3,3,3]  */
+  const float* sfe2_w; const float* sfe2_b;     /* [64,64,3,3] */
+  const float* const* dense_w; const float* const* dense_b;
+  const float* const* lff_w; const float* const* lff_b;
+  const float* gff0_w; const float* gff0_b;     /* [64, 64*num_blocks, 1, 1] */
+  const float* gff1_w; const float* gff1_b;     /* [64,64,3,3] */
+} ciaosr_rdn_desc;
+
+int ciaosr_rdn_plan_bytes(const ciaosr_rdn_desc* desc, size_t* bytes);
+int ciaosr_rdn_plan_init(const ciaosr_rdn_desc* desc, void* plan, size_t plan_bytes, void* stream);
+int ciaosr_rdn_workspace_bytes(const ciaosr_rdn_desc* desc, int B, int H, int W, size_t* bytes);
+/* x [B,3,H,W] (normalised LR image, NCHW fp32) -> feature [B,64,H,W] NCHW fp32 */
+int ciaosr_rdn_forward(const ciaosr_rdn_desc* desc, const void* plan, const float* x, int B, int H,
+                       int W, float* feature, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- tiled inference epilogue (ciaosr.py:218-258, 160-163) -------------- */
 /* acc/cnt [B,3,Ho,Wo] += tile prediction [B, th*tw, 3] placed at (y0,x0).   */

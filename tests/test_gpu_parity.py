@@ -162,3 +162,37 @@ def test_errors_surface_as_python_exceptions():
         g.query_rgb([feat.double()], coord, torch.ones_like(coord))
     with pytest.raises(ValueError):
         g.query_rgb([torch.zeros(1, 4, 6, 6, device=dev)], coord, torch.ones_like(coord))
+
+
+def test_native_rdn_encoder_matches_pytorch():
+    """Encoder fast path: tensor-core RDN vs the PyTorch fp32 encoder (cuDNN, TF32 off)."""
+    from ciaosr_b200.builder import build
+    from ciaosr_b200.generators import LocalImplicitSRRDN
+    dev = _dev()
+    mlp = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3, hidden_list=[256, 256, 256, 256])
+    g = build(dict(type=LocalImplicitSRRDN,
+                   encoder=dict(type="RDN", in_channels=3, out_channels=3, mid_channels=64, num_blocks=3,
+                                upscale_factor=4, num_layers=4, channel_growth=64),
+                   imnet_q=mlp(), imnet_k=mlp(), imnet_v=mlp(), eval_bsize=30000))
+    synth.fill_module(g, 11)
+    g = g.eval().to(dev)
+    for b, h, w in [(2, 20, 17), (1, 48, 48)]:
+        x = synth.synth_lr_image(b, h, w, 11).to(dev)
+        with torch.no_grad():
+            g.native_encoder = False
+            ref = g.gen_feature(x)[0]
+            g.native_encoder = True
+            out = g.gen_feature(x)[0]
+        scale = float(ref.abs().mean())
+        err = max_abs(out, ref)
+        assert out.shape == ref.shape
+        assert err < 2e-5 * max(1.0, scale) + 2e-5, (err, scale)
+        # and through the whole generator
+        coord = make_coord((h * 2, w * 2)).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        cell = make_cell((h * 2, w * 2), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        with torch.no_grad():
+            g.native_encoder = False
+            y0 = g(x, coord, cell, test_mode=True)
+            g.native_encoder = True
+            y1 = g(x, coord, cell, test_mode=True)
+        assert max_abs(y0, y1) < TOL
