@@ -51,6 +51,74 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// ---- epilogue shared by both convolution kernels: one thread per output pixel ------------------------------
+__device__ __forceinline__ void conv_epilogue(const TcShared& s, const ConvParams& P, uint32_t tmem_base, int warp,
+                                              int lane) {
+    const int row = threadIdx.x - EPI_T0;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t job = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++job) {
+      const uint32_t d = job & 1, n = job >> 1;
+      const long long g = (long long)tile * ROWS + row;
+      const int rr = (int)(g % P.HP2P), b = (int)(g / P.HP2P);
+      const int yy = rr / P.P, xx = rr - yy * P.P;
+      const bool valid = g < P.Np && yy >= 1 && yy <= P.H && xx >= 1 && xx <= P.W;
+      mbar_wait(bar_at(s, BAR_D_READY + 2 * d), n & 1, 450);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_taddr + d * 256 + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += s.consts[c0 + i];
+        if (P.res32 != nullptr) {
+          const float4* rp = reinterpret_cast<const float4*>(P.res32 + g * 64 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = __ldg(rp + j);
+            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? (P.relu ? fmaxf(v[i], 0.0f) : v[i]) : 0.0f;
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+        if (P.d1.hi != nullptr) {
+          uint4* ph = reinterpret_cast<uint4*>(P.d1.hi + g * P.d1.ld + P.d1.choff + c0);
+          uint4* pl = reinterpret_cast<uint4*>(P.d1.lo + g * P.d1.ld + P.d1.choff + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+          }
+        }
+        if (P.d2.hi != nullptr) {
+          uint4* ph = reinterpret_cast<uint4*>(P.d2.hi + g * P.d2.ld + P.d2.choff + c0);
+          uint4* pl = reinterpret_cast<uint4*>(P.d2.lo + g * P.d2.ld + P.d2.choff + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+          }
+        }
+        if (P.out32 != nullptr) {
+          float4* po = reinterpret_cast<float4*>(P.out32 + g * 64 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) po[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (P.out_nchw != nullptr && valid) {
+          float* po = P.out_nchw + (((long long)b * 64 + c0) * P.H + (yy - 1)) * P.W + (xx - 1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) po[(long long)i * P.H * P.W] = v[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_at(s, BAR_D_FREE + d));
+    }
+  }
+
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo) {
@@ -134,70 +202,7 @@ conv_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ---- epilogue: one thread per output pixel ----
-    const int row = threadIdx.x - EPI_T0;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t job = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++job) {
-      const uint32_t d = job & 1, n = job >> 1;
-      const long long g = (long long)tile * ROWS + row;
-      const int rr = (int)(g % P.HP2P), b = (int)(g / P.HP2P);
-      const int yy = rr / P.P, xx = rr - yy * P.P;
-      const bool valid = g < P.Np && yy >= 1 && yy <= P.H && xx >= 1 && xx <= P.W;
-      mbar_wait(bar_at(s, BAR_D_READY + 2 * d), n & 1, 450);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        float v[32];
-        tmem_ld32(lane_taddr + d * 256 + c0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += s.consts[c0 + i];
-        if (P.res32 != nullptr) {
-          const float4* rp = reinterpret_cast<const float4*>(P.res32 + g * 64 + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 q = __ldg(rp + j);
-            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = valid ? (P.relu ? fmaxf(v[i], 0.0f) : v[i]) : 0.0f;
-        uint32_t h[16], l[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-        if (P.d1.hi != nullptr) {
-          uint4* ph = reinterpret_cast<uint4*>(P.d1.hi + g * P.d1.ld + P.d1.choff + c0);
-          uint4* pl = reinterpret_cast<uint4*>(P.d1.lo + g * P.d1.ld + P.d1.choff + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
-          }
-        }
-        if (P.d2.hi != nullptr) {
-          uint4* ph = reinterpret_cast<uint4*>(P.d2.hi + g * P.d2.ld + P.d2.choff + c0);
-          uint4* pl = reinterpret_cast<uint4*>(P.d2.lo + g * P.d2.ld + P.d2.choff + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
-          }
-        }
-        if (P.out32 != nullptr) {
-          float4* po = reinterpret_cast<float4*>(P.out32 + g * 64 + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) po[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (P.out_nchw != nullptr && valid) {
-          float* po = P.out_nchw + (((long long)b * 64 + c0) * P.H + (yy - 1)) * P.W + (xx - 1);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) po[(long long)i * P.H * P.W] = v[i];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_at(s, BAR_D_FREE + d));
-    }
+    conv_epilogue(s, P, tmem_base, warp, lane);
   }
   tc_teardown<1>(tmem_base);
 }
@@ -364,12 +369,17 @@ static RdnWs rdn_carve(Arena& a, const ciaosr_rdn_desc* d, int B, int H, int W) 
   return w;
 }
 
-static int launch_conv(const ConvParams& P, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+static int conv_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
     CIAOSR_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr_set = true;
   }
+  return CIAOSR_OK;
+}
+static int launch_conv(const ConvParams& P, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+  int rc = conv_attrs();
+  if (rc) return rc;
   CIAOSR_LAUNCH(conv_tc_kernel, tc_grid_size(P.n_tiles), CONV_THREADS, SM_TOTAL, st, P, mh, ml);
   return CIAOSR_OK;
 }
@@ -468,8 +478,8 @@ int ciaosr_rdn_forward(const ciaosr_rdn_desc* d, const void* plan, const float* 
   ConvParams c{};
   c.n_tiles = (int)(w.Npa / ROWS); c.P = P; c.HP2P = HP2P; c.H = H; c.W = W; c.Np = (int)w.Np;
   // bias rows in the plan: [sfe1, sfe2, dense (block-major), lff (per block), gff0, gff1]
-  auto conv = [&](const CUtensorMap* src, int Cin, int ntaps, size_t blob_off, int bias_row, int relu,
-                  const float* res32, ConvDst d1, ConvDst d2, float* out32, float* out_nchw) -> int {
+  auto conv = [&](const CUtensorMap* src, int Cin, int ntaps, size_t blob_off, int bias_row,
+                  int relu, const float* res32, ConvDst d1, ConvDst d2, float* out32, float* out_nchw) -> int {
     c.ntaps = ntaps; c.cblocks = Cin / 64; c.blob = p + blob_off; c.bias = bias + 64 * bias_row; c.res32 = res32;
     c.relu = relu; c.d1 = d1; c.d2 = d2; c.out32 = out32; c.out_nchw = out_nchw;
     return launch_conv(c, src[0], src[1], st);

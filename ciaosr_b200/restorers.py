@@ -12,6 +12,7 @@ import os.path as osp
 import torch
 import torch.nn as nn
 
+from . import dist as cdist
 from . import native
 from .builder import build_backbone, build_loss
 from .coords import make_coord
@@ -107,11 +108,12 @@ class CiaoSR(BasicRestorer):
         stride = tile - overlap
         return list(range(0, n - tile, stride)) + [n - tile]
 
-    def clip_test(self, img_lq, model, denorm=False, tiles=None):
+    def clip_test(self, img_lq, model, denorm=False):
         """Overlap-average tiled inference (ciaosr.py:218-258) -> [B, Ho*Wo, 3].
 
-        `tiles`: optional subset of tile indices to run (multi-GPU sharding); the
-        accumulators are then returned un-normalised as (acc, cnt).
+        With torch.distributed initialised (one process per GPU) the tiles are dealt round-robin
+        to the ranks, each rank runs the generator on its tiles, ONE all-gather collects the tile
+        predictions, and every rank blends the full frame locally (ciaosr_b200/dist.py).
         """
         sf = self.test_cfg.get("scale", None)
         b, c, h, w = img_lq.size()
@@ -127,14 +129,17 @@ class CiaoSR(BasicRestorer):
         cell = torch.ones_like(hr_coord)
         cell[:, :, 0] *= 2 / th
         cell[:, :, 1] *= 2 / tw
-        for ti, (y0, x0) in enumerate(origins):
-            if tiles is not None and ti not in tiles:
-                continue
+
+        def run_tile(y0, x0):
             patch = img_lq[..., y0:y0 + tile, x0:x0 + tile].contiguous()
-            out = model(patch, hr_coord, cell, test_mode=True)
+            return model(patch, hr_coord, cell, test_mode=True)
+
+        if cdist.world()[1] > 1 and self.test_cfg.get("shard_tiles", True):
+            preds = cdist.sharded_tile_predictions(origins, run_tile, (b, th * tw, 3), img_lq)
+        else:
+            preds = (run_tile(y0, x0) for y0, x0 in origins)
+        for (y0, x0), out in zip(origins, preds):
             native.tile_blend_accumulate(out, acc, cnt, y0 * sf, x0 * sf, th, tw)
-        if tiles is not None:
-            return acc, cnt
         if denorm:
             return native.tile_blend_finish(acc, cnt, self.gt_mean.to(acc), self.gt_std.to(acc), True)
         return native.tile_blend_finish(acc, cnt)

@@ -196,3 +196,32 @@ def test_native_rdn_encoder_matches_pytorch():
             g.native_encoder = True
             y1 = g(x, coord, cell, test_mode=True)
         assert max_abs(y0, y1) < TOL
+
+
+def test_tiled_rdn_engines_agree():
+    """A BASELINE.json config-3 style run in miniature: RDN-CiaoSR, LR 72x80, x2, tile 48 / overlap 16
+    (2x3 tiles) through CiaoSR.forward_test.  The product path (native encoder + tcgen05 engine) must agree
+    with the all-fp32 path (PyTorch encoder + SIMT engine) within the parity tolerance."""
+    from ciaosr_b200.builder import build
+    from ciaosr_b200.generators import LocalImplicitSRRDN
+    from ciaosr_b200.restorers import CiaoSR
+    dev = _dev()
+    mlp = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3, hidden_list=[256, 256, 256, 256])
+    cfg = dict(type=CiaoSR,
+               generator=dict(type=LocalImplicitSRRDN,
+                              encoder=dict(type="RDN", in_channels=3, out_channels=3, mid_channels=64, num_blocks=2,
+                                           upscale_factor=4, num_layers=3, channel_growth=64),
+                              imnet_q=mlp(), imnet_k=mlp(), imnet_v=mlp(), eval_bsize=30000),
+               rgb_mean=(0.4488, 0.4371, 0.4040), rgb_std=(1., 1., 1.), pixel_loss=dict(type="L1Loss"))
+    m = build(cfg, test_cfg=dict(scale=2, tile=48, tile_overlap=16))
+    synth.fill_module(m.generator, 5)
+    m = m.eval().to(dev)
+    lq = (synth.synth_lr_image(1, 72, 80, 5) + torch.tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1)).to(dev)
+    outs = []
+    for native_enc, engine in [(True, "tcgen05"), (False, "simt")]:
+        m.generator.native_encoder = native_enc
+        m.generator.engine = engine
+        outs.append(m(lq=lq, gt=None, test_mode=True)["output"])
+    assert outs[0].shape == (1, 3, 144, 160)
+    assert float(outs[0].min()) >= 0.0 and float(outs[0].max()) <= 1.0
+    assert max_abs(outs[0], outs[1]) < TOL
