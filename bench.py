@@ -8,7 +8,8 @@ growth 64; imnet_{q,k,v} hidden 256x4; cross-scale attention on), a batch of 16 
 48x48 crops -> x4 (192x192), i.e. 589 824 HR pixels per step per GPU, eval_bsize 30000,
 synthetic weights and inputs (the reference ships no checkpoints or data).
 
-A step = one `generator(lq, coord, cell, test_mode=True)` call: the PyTorch RDN encoder
+A step = one `generator(lq, coord, cell, test_mode=True)` call: the RDN encoder (native
+tcgen05 implicit-GEMM path, csrc/rdn_tc.cu; `--native-encoder 0` keeps PyTorch/cuDNN)
 followed by the native head.  `value` times it with inputs resident in HBM; `e2e` times the
 restorer call a user makes (`model(lq, test_mode=True, coord=, cell=)`, ciaosr.py:111-203)
 from pinned host buffers, result back on the host.  N > 1: weak scaling, every rank runs its
@@ -204,6 +205,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the generator forward as a CUDA graph")
     ap.add_argument("--channels-last", type=int, default=1, help="PyTorch encoder in channels_last")
+    ap.add_argument("--native-encoder", type=int, default=1, help="RDN encoder on the native tcgen05 path")
     ap.add_argument("--encoder-tf32", type=int, default=0,
                     help="allow TF32 cuDNN convolutions in the PyTorch encoder (PyTorch's default is 1; 0 keeps the "
                          "encoder fp32 so that end-to-end outputs match the fp32 reference)")
@@ -233,6 +235,7 @@ def main():
         gen.to(memory_format=torch.channels_last)
     gen.channels_last = bool(args.channels_last)
     gen.cuda_graph = bool(args.cuda_graph)
+    gen.native_encoder = "auto" if args.native_encoder else False
     lq_h, coord_h, cell_h = make_inputs(B, 100 + rank)
     lq_h, coord_h, cell_h = lq_h.pin_memory(), coord_h.pin_memory(), cell_h.pin_memory()
     lq_d = ((lq_h - torch.tensor(RGB_MEAN).view(1, 3, 1, 1))).to(dev)     # normalised, as forward_test passes it
@@ -344,8 +347,10 @@ def main():
                        "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB",
                        "head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
                        "head_ms": ms_head, "eager_step_ms": ms_eager, "encoder_ms_est": ms_enc,
-                       "encoder": "PyTorch RDN fp32 (cudnn.allow_tf32=%s, channels_last=%s)"
-                                  % (torch.backends.cudnn.allow_tf32, bool(args.channels_last)),
+                       "encoder": ("native RDN on tcgen05 (bf16x3 implicit GEMM, fp32-grade; csrc/rdn_tc.cu)"
+                                   if getattr(gen, "native_encoder", False) else
+                                   "PyTorch RDN fp32 (cudnn.allow_tf32=%s, channels_last=%s)"
+                                   % (torch.backends.cudnn.allow_tf32, bool(args.channels_last))),
                        "cuda_graph": bool(args.cuda_graph)},
             "clocks": clocks,
             "e2e": {"value": world * npx / (ms_e2e * 1e-3) / 1e6, "unit": "Mpix/s",
