@@ -383,3 +383,18 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
 }
 
 }  // namespace ciaosr
+
+#ifdef CIAOSR_TC_TIMING
+// diagnostic build only: cycles spent in mbarrier waits by the kernels of this translation unit
+extern "C" int ciaosr_debug_wait_read_head(unsigned long long* cycles, unsigned long long* counts, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(cycles, ciaosr::tc::g_wait_cycles, 64 * 8);
+  cudaMemcpyFromSymbol(counts, ciaosr::tc::g_wait_count, 64 * 8);
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_cycles, z, 64 * 8);
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_count, z, 64 * 8);
+  }
+  return 0;
+}
+#endif

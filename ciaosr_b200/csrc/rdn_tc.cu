@@ -22,6 +22,7 @@
 // channels into its slice; the LFF output goes straight into the next block's buffer and the global
 // fusion buffer.  The residual trunk is kept in fp32.
 #include <cuda.h>
+#include <cstdlib>
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -52,7 +53,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 
 // ---- epilogue shared by both convolution kernels: one thread per output pixel ------------------------------
-__device__ __forceinline__ void conv_epilogue(const TcShared& s, const ConvParams& P, uint32_t tmem_base, int warp,
+struct ConvEpiBars { const float* bias_s; uint32_t d_ready[2]; uint32_t d_free[2]; bool stacked; };
+__device__ __forceinline__ void conv_epilogue(const ConvEpiBars& s, const ConvParams& P, uint32_t tmem_base, int warp,
                                               int lane) {
     const int row = threadIdx.x - EPI_T0;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -63,14 +65,20 @@ __device__ __forceinline__ void conv_epilogue(const TcShared& s, const ConvParam
       const int rr = (int)(g % P.HP2P), b = (int)(g / P.HP2P);
       const int yy = rr / P.P, xx = rr - yy * P.P;
       const bool valid = g < P.Np && yy >= 1 && yy <= P.H && xx >= 1 && xx <= P.W;
-      mbar_wait(bar_at(s, BAR_D_READY + 2 * d), n & 1, 450);
+      mbar_wait(s.d_ready[d], n & 1, 450);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         float v[32];
         tmem_ld32(lane_taddr + d * 256 + c0, v);
+        if (s.stacked) {                 // the A.W_lo partial sums live 64 columns further
+          float u[32];
+          tmem_ld32(lane_taddr + d * 256 + 64 + c0, u);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += s.consts[c0 + i];
+          for (int i = 0; i < 32; ++i) v[i] += u[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += s.bias_s[c0 + i];
         if (P.res32 != nullptr) {
           const float4* rp = reinterpret_cast<const float4*>(P.res32 + g * 64 + c0);
 #pragma unroll
@@ -115,7 +123,7 @@ __device__ __forceinline__ void conv_epilogue(const TcShared& s, const ConvParam
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_at(s, BAR_D_FREE + d));
+      if (lane == 0) mbar_arrive(s.d_free[d]);
     }
   }
 
@@ -202,9 +210,126 @@ conv_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
       __syncwarp();
     }
   } else if (warp >= 4) {
-    conv_epilogue(s, P, tmem_base, warp, lane);
+    const ConvEpiBars eb{s.consts, {bar_at(s, BAR_D_READY), bar_at(s, BAR_D_READY + 2)},
+                         {bar_at(s, BAR_D_FREE), bar_at(s, BAR_D_FREE + 1)}, false};
+    conv_epilogue(eb, P, tmem_base, warp, lane);
   }
   tc_teardown<1>(tmem_base);
+}
+
+// ---- 3x3 convolution with halo staging ("conv3") ------------------------------------------------------------
+// The nine taps of a 3x3 convolution read the same pixels shifted by dy*P + dx rows of the linearised
+// layout, so ONE TMA box of HR = 128 + 2P + 2 rows per (tile, 64-channel block) serves all of them: tap
+// (dy, dx) is the same smem tile read through a UMMA descriptor whose start address is advanced by
+// r0 = (dy+1)*P + (dx+1) rows of 128 bytes.  The 128B swizzle is a function of the absolute smem address
+// (bits 4-6 ^= bits 7-9), for the TMA write and the UMMA read alike, so a start address that is not
+// 1024-byte aligned needs nothing else: the descriptor's base-offset field stays 0 (measured on B200:
+// base offset = r0 & 7, the other reading of the PTX text, gives wrong sums).  L2 -> SM traffic per (tile, channel block) drops from
+// 9 x (32 KB A + 16 KB W) = 432 KB to 2 x HR x 128 B (59 KB at P = 50) + 144 KB of weights.
+// Needs HR <= 256 (TMA box limit), i.e. W <= 61; wider images use the per-tap kernel above.
+constexpr int C3_A_HALF = 256 * 128;                     // bytes reserved per hi (or lo) halo tile
+constexpr int C3_A_STAGES = 2, C3_W_STAGES = 5;
+constexpr int C3_SM_W = C3_A_STAGES * 2 * C3_A_HALF;     // 128 KB of A stages first
+constexpr int C3_SM_CONST = C3_SM_W + C3_W_STAGES * SLAB_BYTES;
+constexpr int C3_SM_BAR = C3_SM_CONST + 64 * 4;
+constexpr int C3_W_FULL = 0, C3_W_EMPTY = 5, C3_A_READY = 10, C3_A_FREE = 12, C3_D_READY = 14, C3_D_FREE = 16,
+              C3_NBARS = 18;
+constexpr int C3_SM_SLOT = C3_SM_BAR + C3_NBARS * 8;
+constexpr int C3_SM_TOTAL = C3_SM_SLOT + 16;
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3_tc_kernel(const ConvParams P, const int HR, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + C3_SM_BAR;
+  float* bias_s = reinterpret_cast<float*>(smem + C3_SM_CONST);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = P.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C3_W_STAGES; ++i) { mbar_init(bars + 8 * (C3_W_FULL + i), 1); mbar_init(bars + 8 * (C3_W_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + 8 * (C3_A_READY + i), 1); mbar_init(bars + 8 * (C3_A_FREE + i), 1);
+      mbar_init(bars + 8 * (C3_D_READY + i), 1); mbar_init(bars + 8 * (C3_D_FREE + i), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(sbase + C3_SM_SLOT, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + C3_SM_SLOT);
+
+  if (warp == 0) {
+    // ---- producer: one halo box (hi, lo) per channel block, one 16 KB weight slab per tap ----
+    uint32_t acnt = 0, wcnt = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int cb = 0; cb < P.cblocks; ++cb, ++acnt) {
+        const int ast = acnt & 1;
+        mbar_wait(bars + 8 * (C3_A_FREE + ast), ((acnt >> 1) & 1) ^ 1, 400 + ast);
+        if (lane == 0) {
+          const uint32_t full = bars + 8 * (C3_A_READY + ast);
+          mbar_arrive_expect_tx(full, 2u * (uint32_t)HR * 128u);
+          const int pix = tile * ROWS - P.P - 1;
+          tma_load_2d(sbase + (2 * ast) * C3_A_HALF, &map_hi, cb * 64, pix, full);
+          tma_load_2d(sbase + (2 * ast + 1) * C3_A_HALF, &map_lo, cb * 64, pix, full);
+        }
+        __syncwarp();
+        for (int tap = 0; tap < 9; ++tap, ++wcnt) {
+          const int wst = wcnt % C3_W_STAGES;
+          mbar_wait(bars + 8 * (C3_W_EMPTY + wst), ((wcnt / C3_W_STAGES) & 1) ^ 1, 410 + wst);
+          if (lane == 0) {
+            const uint32_t full = bars + 8 * (C3_W_FULL + wst);
+            mbar_arrive_expect_tx(full, SLAB_BYTES);
+            bulk_g2s(sbase + C3_SM_W + wst * SLAB_BYTES, P.blob + (size_t)(cb * 9 + tap) * SLAB_BYTES, SLAB_BYTES, full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- UMMA issuer ----
+    const uint32_t idesc = make_idesc_bf16(ROWS, 128);   // D[:, 0:64] = A.W_hi, D[:, 64:128] = A.W_lo (summed in the epilogue)
+    uint32_t acnt = 0, wcnt = 0, job = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++job) {
+      const uint32_t d = job & 1, n = job >> 1;
+      mbar_wait(bars + 8 * (C3_D_FREE + d), (n + 1) & 1, 420);
+      tc_fence_after();
+      const uint32_t dcol = tmem_base + d * 256;
+      for (int cb = 0; cb < P.cblocks; ++cb, ++acnt) {
+        const int ast = acnt & 1;
+        mbar_wait(bars + 8 * (C3_A_READY + ast), (acnt >> 1) & 1, 430 + ast);
+        for (int tap = 0; tap < 9; ++tap, ++wcnt) {
+          const int wst = wcnt % C3_W_STAGES;
+          mbar_wait(bars + 8 * (C3_W_FULL + wst), (wcnt / C3_W_STAGES) & 1, 440 + wst);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t r0 = (uint32_t)((tap / 3) * P.P + tap % 3);
+            const uint32_t a_hi = desc_lo(sbase + (2 * ast) * C3_A_HALF + r0 * 128u);
+            const uint32_t a_lo = desc_lo(sbase + (2 * ast + 1) * C3_A_HALF + r0 * 128u);
+            const uint32_t b = desc_lo(sbase + C3_SM_W + wst * SLAB_BYTES);     // 128 rows: [W_hi (64); W_lo (64)]
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_lo(dcol, a_lo + 2 * ks, b + 2 * ks, idesc, (cb | tap | ks) != 0 ? 1u : 0u);
+              umma_lo(dcol, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
+            }
+            umma_commit(bars + 8 * (C3_W_EMPTY + wst));
+            if (tap == 8) umma_commit(bars + 8 * (C3_A_FREE + ast));
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) umma_commit(bars + 8 * (C3_D_READY + d));
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const ConvEpiBars eb{bias_s, {bars + 8 * C3_D_READY, bars + 8 * (C3_D_READY + 1)},
+                         {bars + 8 * C3_D_FREE, bars + 8 * (C3_D_FREE + 1)}, true};
+    conv_epilogue(eb, P, tmem_base, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---- weight packing: conv weight [64, Cin, kh, kw] -> per K-slab (cblock, tap): hi 64x64 | lo 64x64 ----------
@@ -334,13 +459,13 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// 2-D map over a bf16 [pixels, channels] tensor: box = 64 channels x 128 pixels, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* m, void* base, long long pixels, int channels) {
+// 2-D map over a bf16 [pixels, channels] tensor: box = 64 channels x `rows` pixels, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* m, void* base, long long pixels, int channels, int rows = 128) {
   EncodeTiledFn enc = get_encode();
   CIAOSR_REQUIRE(enc != nullptr, CIAOSR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)pixels};
   const cuuint64_t gstride[1] = {(cuuint64_t)channels * 2};
-  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -381,6 +506,20 @@ static int launch_conv(const ConvParams& P, const CUtensorMap& mh, const CUtenso
   int rc = conv_attrs();
   if (rc) return rc;
   CIAOSR_LAUNCH(conv_tc_kernel, tc_grid_size(P.n_tiles), CONV_THREADS, SM_TOTAL, st, P, mh, ml);
+  return CIAOSR_OK;
+}
+// rows of the halo box of conv3_tc_kernel for pitch P (0: image too wide for one TMA box)
+static int conv3_halo_rows(int P) {
+  const int hr = (ROWS + 2 * P + 2 + 7) / 8 * 8;
+  return hr <= 256 ? hr : 0;
+}
+static int launch_conv3(const ConvParams& P, int HR, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SM_TOTAL));
+    attr_set = true;
+  }
+  CIAOSR_LAUNCH(conv3_tc_kernel, tc_grid_size(P.n_tiles), CONV_THREADS, C3_SM_TOTAL, st, P, HR, mh, ml);
   return CIAOSR_OK;
 }
 
@@ -467,6 +606,16 @@ int ciaosr_rdn_forward(const ciaosr_rdn_desc* d, const void* plan, const float* 
       return rc;
   if ((rc = make_map(&m_gf[0], w.gfh, w.Npa, 64 * nb)) || (rc = make_map(&m_gf[1], w.gfl, w.Npa, 64 * nb))) return rc;
   if ((rc = make_map(&m_g1[0], w.g1h, w.Npa, 64)) || (rc = make_map(&m_g1[1], w.g1l, w.Npa, 64))) return rc;
+  // halo boxes for the 3x3 layers (conv3_tc_kernel), when the image is narrow enough for one box
+  const int HR = conv3_halo_rows(W + 2);
+  CUtensorMap h_f1[2], h_rb[2][2], h_g1[2];
+  if (HR) {
+    if ((rc = make_map(&h_f1[0], w.f1h, w.Npa, 64, HR)) || (rc = make_map(&h_f1[1], w.f1l, w.Npa, 64, HR))) return rc;
+    for (int i = 0; i < 2; ++i)
+      if ((rc = make_map(&h_rb[i][0], w.rbh[i], w.Npa, cbuf, HR)) || (rc = make_map(&h_rb[i][1], w.rbl[i], w.Npa, cbuf, HR)))
+        return rc;
+    if ((rc = make_map(&h_g1[0], w.g1h, w.Npa, 64, HR)) || (rc = make_map(&h_g1[1], w.g1l, w.Npa, 64, HR))) return rc;
+  }
 
   // sfe1: 3 -> 64 from the NCHW image (padding pixels of its outputs are zeroed first)
   CIAOSR_CUDA_OK(cudaMemsetAsync(w.f1h, 0, (size_t)w.Npa * 64 * 2, st));
@@ -478,32 +627,47 @@ int ciaosr_rdn_forward(const ciaosr_rdn_desc* d, const void* plan, const float* 
   ConvParams c{};
   c.n_tiles = (int)(w.Npa / ROWS); c.P = P; c.HP2P = HP2P; c.H = H; c.W = W; c.Np = (int)w.Np;
   // bias rows in the plan: [sfe1, sfe2, dense (block-major), lff (per block), gff0, gff1]
-  auto conv = [&](const CUtensorMap* src, int Cin, int ntaps, size_t blob_off, int bias_row,
+  auto conv = [&](const CUtensorMap* src, const CUtensorMap* halo, int Cin, int ntaps, size_t blob_off, int bias_row,
                   int relu, const float* res32, ConvDst d1, ConvDst d2, float* out32, float* out_nchw) -> int {
     c.ntaps = ntaps; c.cblocks = Cin / 64; c.blob = p + blob_off; c.bias = bias + 64 * bias_row; c.res32 = res32;
     c.relu = relu; c.d1 = d1; c.d2 = d2; c.out32 = out32; c.out_nchw = out_nchw;
+    if (ntaps == 9 && HR && halo != nullptr) return launch_conv3(c, HR, halo[0], halo[1], st);
     return launch_conv(c, src[0], src[1], st);
   };
   const int row_dense = 2, row_lff = 2 + nb * nl, row_gff = 2 + nb * nl + nb;
   const ConvDst none{nullptr, nullptr, 0, 0};
   // sfe2: F1 -> first 64 channels of RDB buffer 0 (+ fp32 trunk copy)
-  if ((rc = conv(m_f1, 64, 9, L.sfe2, 1, 0, nullptr, ConvDst{w.rbh[0], w.rbl[0], cbuf, 0}, none, w.xr[0], nullptr)))
+  if ((rc = conv(m_f1, h_f1, 64, 9, L.sfe2, 1, 0, nullptr, ConvDst{w.rbh[0], w.rbl[0], cbuf, 0}, none, w.xr[0], nullptr)))
     return rc;
   for (int r = 0; r < nb; ++r) {
     const int cur = r & 1, nxt = cur ^ 1;
     for (int l = 0; l < nl; ++l)       // dense layer: conv3x3 + ReLU over channels [0, 64(1+l)) -> slice l+1
-      if ((rc = conv(m_rb[cur], 64 * (1 + l), 9, L.dense0 + r * L.dense_stride_block + L.dense_off[l], row_dense + r * nl + l, 1, nullptr,
+      if ((rc = conv(m_rb[cur], h_rb[cur], 64 * (1 + l), 9, L.dense0 + r * L.dense_stride_block + L.dense_off[l], row_dense + r * nl + l, 1, nullptr,
                      ConvDst{w.rbh[cur], w.rbl[cur], cbuf, 64 * (1 + l)}, none, nullptr, nullptr))) return rc;
     // local feature fusion 1x1 + residual (fp32 trunk) -> next block's input slice and the global fusion buffer
-    if ((rc = conv(m_rb[cur], cbuf, 1, L.lff0 + (size_t)r * (1 + nl) * SLAB_BYTES, row_lff + r, 0, w.xr[cur],
+    if ((rc = conv(m_rb[cur], nullptr, cbuf, 1, L.lff0 + (size_t)r * (1 + nl) * SLAB_BYTES, row_lff + r, 0, w.xr[cur],
                    ConvDst{w.rbh[nxt], w.rbl[nxt], cbuf, 0}, ConvDst{w.gfh, w.gfl, 64 * nb, 64 * r}, w.xr[nxt],
                    nullptr))) return rc;
   }
   // global feature fusion: 1x1 over all block outputs, then 3x3, + sfe1 output -> feature (NCHW fp32)
-  if ((rc = conv(m_gf, 64 * nb, 1, L.gff0, row_gff, 0, nullptr, ConvDst{w.g1h, w.g1l, 64, 0}, none, nullptr, nullptr)))
+  if ((rc = conv(m_gf, nullptr, 64 * nb, 1, L.gff0, row_gff, 0, nullptr, ConvDst{w.g1h, w.g1l, 64, 0}, none, nullptr, nullptr)))
     return rc;
-  if ((rc = conv(m_g1, 64, 9, L.gff1, row_gff + 1, 0, w.f1_32, none, none, nullptr, feature))) return rc;
+  if ((rc = conv(m_g1, h_g1, 64, 9, L.gff1, row_gff + 1, 0, w.f1_32, none, none, nullptr, feature))) return rc;
   return CIAOSR_OK;
 }
 
 }  // extern "C"
+
+#ifdef CIAOSR_TC_TIMING
+extern "C" int ciaosr_debug_wait_read_rdn(unsigned long long* cycles, unsigned long long* counts, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(cycles, ciaosr::tc::g_wait_cycles, 64 * 8);
+  cudaMemcpyFromSymbol(counts, ciaosr::tc::g_wait_count, 64 * 8);
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_cycles, z, 64 * 8);
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_count, z, 64 * 8);
+  }
+  return 0;
+}
+#endif

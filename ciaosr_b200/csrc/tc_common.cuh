@@ -45,8 +45,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef CIAOSR_TC_TIMING
+// Diagnostic build only (tools/wait_breakdown.py): cycles each warp spends in mbarrier waits, by tag / 10.
+static __device__ unsigned long long g_wait_cycles[64];
+static __device__ unsigned long long g_wait_count[64];
+__device__ __forceinline__ void tc_time_add(int cls, long long t0) {
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&g_wait_cycles[cls & 63], (unsigned long long)(clock64() - t0));
+    atomicAdd(&g_wait_count[cls & 63], 1ull);
+  }
+}
+#endif
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+#ifdef CIAOSR_TC_TIMING
+  const long long tt = clock64();
+  struct Rec { int tag; long long t; __device__ ~Rec() { tc_time_add(tag / 10, t); } } rec{tag, tt};
+#endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;

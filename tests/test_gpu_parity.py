@@ -176,7 +176,7 @@ def test_native_rdn_encoder_matches_pytorch():
                    imnet_q=mlp(), imnet_k=mlp(), imnet_v=mlp(), eval_bsize=30000))
     synth.fill_module(g, 11)
     g = g.eval().to(dev)
-    for b, h, w in [(2, 20, 17), (1, 48, 48)]:
+    for b, h, w in [(2, 20, 17), (1, 48, 48), (1, 12, 70)]:       # W = 70: too wide for the halo box, per-tap kernel
         x = synth.synth_lr_image(b, h, w, 11).to(dev)
         with torch.no_grad():
             g.native_encoder = False
