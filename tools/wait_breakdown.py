@@ -10,7 +10,8 @@ from ciaosr_b200 import _lib
 
 NAMES = {10: "producer: W_EMPTY", 20: "issuer: D_FREE", 21: "issuer: A_READY", 22: "issuer: W_FULL",
          30: "rows: A_FREE", 31: "rows: D_READY", 40: "conv producer: A_FREE", 41: "conv producer: W_EMPTY",
-         42: "conv issuer: D_FREE", 43: "conv issuer: A_READY", 44: "conv issuer: W_FULL", 45: "conv rows: D_READY"}
+         42: "conv issuer: D_FREE", 43: "conv issuer: A_READY", 44: "conv issuer: W_FULL", 45: "conv rows: D_READY",
+         46: "conv stagers: W_EMPTY"}
 dev = torch.device("cuda:0")
 model = bench.build_model("auto").to(dev)
 lq, coord, cell = bench.make_inputs(bench.B, 100)
