@@ -112,6 +112,12 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(slot);
+  // Programmatic dependent launch: the next layer's CTAs may take over this SM as soon as this CTA exits (their
+  // prologue and weight prefetch overlap this layer's tail); everything that touches the previous layer's output
+  // -- the TMA producer and the epilogue (residual reads, all writes) -- first waits for that grid to complete.
+  // The weight stagers read constants only and start right away.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp < 8) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int units = P.cblocks * P.ntaps;                     // K-slabs per tile
   const int tiles_per_image = P.tiles_x * P.tiles_y;
   const int halo = P.ntaps == 9 ? 1 : 0;
@@ -477,7 +483,16 @@ static int launch_convw(ConvParams P, const MapPair& mp, cudaStream_t st) {
     CIAOSR_CUDA_OK(cudaFuncSetAttribute(convw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     max_set = smem_bytes;
   }
-  CIAOSR_LAUNCH(convw_tc_kernel, tc_grid_size(P.n_tiles), CW_THREADS, smem_bytes, st, P, mp.m[k][0], mp.m[k][1]);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tc_grid_size(P.n_tiles)); cfg.blockDim = dim3(CW_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, convw_tc_kernel, P, mp.m[k][0], mp.m[k][1]);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CIAOSR_REQUIRE(e == cudaSuccess, CIAOSR_E_CUDA, "launch of convw_tc_kernel failed: %s", cudaGetErrorString(e));
   return CIAOSR_OK;
 }
 
