@@ -385,6 +385,17 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
 }  // namespace ciaosr
 
 #ifdef CIAOSR_TC_TIMING
+extern "C" int ciaosr_debug_trace(int on, unsigned long long* out, unsigned int* n) {
+  cudaDeviceSynchronize();
+  if (out) {
+    cudaMemcpyFromSymbol(n, ciaosr::tc::g_trace_n, 4);
+    cudaMemcpyFromSymbol(out, ciaosr::tc::g_trace, 2 * 8192 * 8);
+  }
+  unsigned int z = 0;
+  cudaMemcpyToSymbol(ciaosr::tc::g_trace_n, &z, 4);
+  cudaMemcpyToSymbol(ciaosr::tc::g_trace_req, &on, 4);
+  return 0;
+}
 // diagnostic build only: cycles spent in mbarrier waits by the kernels of this translation unit
 extern "C" int ciaosr_debug_wait_read_head(unsigned long long* cycles, unsigned long long* counts, int reset) {
   cudaDeviceSynchronize();

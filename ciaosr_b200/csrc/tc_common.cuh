@@ -56,6 +56,22 @@ __device__ __forceinline__ void tc_time_add(int cls, long long t0) {
   }
 }
 #endif
+#ifdef CIAOSR_TC_TIMING
+// timeline trace of CTA 0 (issuer warp and first row warp): (tag, clock) events, tools/trace_pair.py
+static __device__ unsigned long long g_trace[2 * 8192];
+static __device__ unsigned int g_trace_n;
+static __device__ int g_trace_on;
+static __device__ int g_trace_req;        // host request; the traced kernel copies it into g_trace_on
+__device__ __forceinline__ void tc_trace(int tag) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_on) {
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 8192) { g_trace[2 * i] = (unsigned long long)tag; g_trace[2 * i + 1] = (unsigned long long)clock64(); }
+  }
+}
+#define TC_TRACE(tag) ::ciaosr::tc::tc_trace(tag)
+#else
+#define TC_TRACE(tag) do {} while (0)
+#endif
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
 #ifdef CIAOSR_TC_TIMING

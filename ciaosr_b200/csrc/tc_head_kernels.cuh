@@ -63,7 +63,7 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
     }
     slab_begin(s, e, sl, false);
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    if (sl & 1) slabs_done2(s, sl - 1, sl);
+    slab_done(s, sl);
   }
 }
 
@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcShared s = tc_carve(smem);
   for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+#ifdef CIAOSR_TC_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
+#endif
   const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks5 = (P.units5 + 1) / 2;
@@ -126,14 +129,18 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
       else { p.pix = -1; p.gidx = -1; p.rel_y = p.rel_x = p.sc_y = p.sc_x = 0.0f; }
 
       // ---- key chain -----------------------------------------------------------------------
+      if (threadIdx.x == EPI_T0) TC_TRACE(3000);       // tile start
       gen_layer1(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
+      if (threadIdx.x == EPI_T0) TC_TRACE(3001);       // k.L1 written
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 5 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 6 * HID);
       // k.L4 is complete once both accumulator halves are; that also frees the operand slabs, so the value
       // chain's layer 1 is built FIRST: the UMMAs of v.L2 then run while the logits are reduced from D.
       const uint32_t dk = epi_wait_half(s, e, 0);
       epi_wait_half(s, e, 1);
+      if (threadIdx.x == EPI_T0) TC_TRACE(3002);       // k.L4 complete
       gen_layer1(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      if (threadIdx.x == EPI_T0) TC_TRACE(3003);       // v.L1 written
       float logit = 0.0f;
       {
         const uint32_t d = dk;
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
         a = valid ? __fdiv_rn(ex, sum) : 0.0f;
       }
 
+      if (threadIdx.x == EPI_T0) TC_TRACE(3004);       // softmax done
       // ---- value chain (layer 1 was built above) ----------------------------------------------------
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 13 * HID);
       epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 14 * HID);
@@ -278,6 +286,10 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
       }
     }
   }
+#ifdef CIAOSR_TC_TIMING
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = 0;
+#endif
   tc_teardown<CL>(tmem_base);
 }
 

@@ -168,6 +168,7 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
       mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
       m.aready_bits ^= 1u << slot;
     }
+    TC_TRACE(1000 + sl);          // issuer: operand slab sl available
     const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
     // W_hi (stages 0,1): A_lo.W_hi (small term first) and A_hi.W_hi
     mbar_wait(bar_at(s, BAR_W_FULL + 0), m.wphase, 220);
@@ -202,6 +203,7 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
     if (units == 2) umma_commit(bar_at(s, BAR_D_READY + 2 * d + 1));   // waited on only by 2-unit jobs
   }
   __syncwarp();
+  TC_TRACE(1010);                 // issuer: job fully issued
   ++m.jobctr;
 }
 
@@ -318,6 +320,7 @@ __device__ __forceinline__ uint32_t epi_wait_half(const TcShared& s, EpiState& e
   mbar_wait(bar_at(s, BAR_D_READY + b), (e.dready_bits >> b) & 1, 310 + b);
   e.dready_bits ^= 1u << b;
   tc_fence_after();
+  if (threadIdx.x == EPI_T0) TC_TRACE(2000 + nh);      // rows: accumulator half nh observed complete
   return d;
 }
 __device__ __forceinline__ uint32_t epi_wait_d(const TcShared& s, EpiState& e, int units) {
@@ -331,6 +334,7 @@ __device__ __forceinline__ void epi_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
 }
 __device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
+  if (threadIdx.x == EPI_T0) TC_TRACE(2010);           // rows: accumulator drained
   tc_fence_before();
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar_at(s, BAR_D_FREE + (e.jobctr & 1)));
@@ -370,7 +374,7 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
       v[4 * j + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 3]) + b4.w, 0.0f);
     }
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
-    if (HALVES == 2) { if (c & 1) slabs_done2(s, sl - 1, sl); }      // one proxy fence per accumulator half
+    if (HALVES == 2) slab_done(s, sl);      // per slab: the next layer's first UMMAs start one slab earlier (-3 % kernel time)
     else if (c & 1) slab_done(s, sl);
   }
   epi_release_d(s, e);

@@ -1,0 +1,28 @@
+"""Diagnostic (GPU box, timing build): timeline of CTA 0 of pair_mlp_kernel -- issuer warp and first row warp.
+    CIAOSR_LIB=ciaosr_b200/csrc/libciaosr_b200_timing.so python tools/trace_pair.py > gpurun_out/trace.txt"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from ciaosr_b200 import _lib
+dev = torch.device("cuda:0")
+model = bench.build_model("auto").to(dev)
+lq, coord, cell = bench.make_inputs(bench.B, 100)
+lq = (lq - torch.tensor(bench.RGB_MEAN).view(1, 3, 1, 1)).to(dev)
+coord, cell = coord.to(dev), cell.to(dev)
+lib = _lib.load()
+buf = (ctypes.c_ulonglong * (2 * 8192))(); n = ctypes.c_uint(0)
+with torch.no_grad():
+    for _ in range(2):
+        model.generator(lq, coord, cell, test_mode=True)
+    lib.ciaosr_debug_trace(1, None, None)
+    model.generator(lq, coord, cell, test_mode=True)
+    torch.cuda.synchronize()
+lib.ciaosr_debug_trace(0, buf, ctypes.byref(n))
+ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(min(n.value, 8192)))
+t0 = ev[0][0]
+NAMES = {1010: "ISSUER job issued", 2010: "rows  D drained", 3000: "rows  TILE START", 3001: "rows  k.L1 written",
+         3002: "rows  k.L4 complete", 3003: "rows  v.L1 written", 3004: "rows  softmax done"}
+for t, tag in ev:
+    name = NAMES.get(tag) or (f"ISSUER slab {tag - 1000} ready" if 1000 <= tag < 1010 else f"rows  D half {tag - 2000} ready")
+    print(f"{t - t0:10d}  {name}")
