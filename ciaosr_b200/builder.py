@@ -73,8 +73,8 @@ def build_loss(cfg):
 
 
 def _populate():
-    from . import encoders, refiners
-    _REGISTRY.update({"RDN": encoders.RDN, "EDSR": encoders.EDSR,
+    from . import encoders, refiners, swinir
+    _REGISTRY.update({"RDN": encoders.RDN, "EDSR": encoders.EDSR, "SwinIR": swinir.SwinIR,
                       "MLPRefiner": refiners.MLPRefiner, "L1Loss": L1Loss})
 
 

@@ -5,6 +5,7 @@ basic_restorer.py:16-124).  Inference side only: ``forward(test_mode=True)``,
 drop-in boundary; the tile blend + de-normalise + clamp epilogue runs in two small
 native kernels instead of the reference's Python double loop over full-frame masks.
 """
+import copy
 import math
 import numbers
 import os.path as osp
@@ -63,11 +64,12 @@ class CiaoSR(BasicRestorer):
         self.lq_mean, self.lq_std = self.lq_mean.to(lq), self.lq_std.to(lq)
         lq = (lq - self.lq_mean) / self.lq_std
         self.gt_mean, self.gt_std = self.gt_mean.to(lq), self.gt_std.to(lq)
+        model = self._test_generator()
         with torch.no_grad():
             if self.test_cfg is not None and self.test_cfg.get("tile", None):
-                pred = self.clip_test(lq, self.generator, denorm=True)
+                pred = self.clip_test(lq, model, denorm=True)
             else:
-                pred = self.generator(lq, coord, cell, test_mode=True)
+                pred = model(lq, coord, cell, test_mode=True)
                 pred = pred * self.gt_std + self.gt_mean
                 pred.clamp_(0, 1)
         ih, iw = lq.shape[-2:]
@@ -101,6 +103,9 @@ class CiaoSR(BasicRestorer):
 
     def init_weights(self, pretrained=None, strict=True):
         self.generator.init_weights(pretrained, strict)
+
+    def _test_generator(self):
+        return self.generator
 
     @staticmethod
     def tile_origins(n, tile, overlap):
@@ -143,3 +148,40 @@ class CiaoSR(BasicRestorer):
         if denorm:
             return native.tile_blend_finish(acc, cnt, self.gt_mean.to(acc), self.gt_std.to(acc), True)
         return native.tile_blend_finish(acc, cnt)
+
+
+class RealCiaoSR(CiaoSR):
+    """Real-world variant (mmedited/models/restorers/real_ciaosr.py:28-373, configs/002_*.py): same
+    inference path as ``CiaoSR`` but evaluated through the EMA copy of the generator
+    (``generator_ema``, real_ciaosr.py:84-87, 262) -- its weights are what the released real-world
+    checkpoints are tested with, so both copies appear in ``state_dict`` under the reference's names
+    together with the ``step_counter`` buffer.  Its ``clip_test`` (real_ciaosr.py:336-373) is the same
+    overlap-average blend as ``CiaoSR.clip_test`` for batch 1 (it builds batch-1 coordinates with
+    ``.cuda()``); the batched form above covers it.
+
+    The GAN-training pieces (discriminator, GAN / perceptual losses, the sharpened-GT switches, the
+    degradation queue in ``train_step``) are outside the inference scope: their configs are accepted and
+    kept as attributes, never built.
+    """
+
+    def __init__(self, generator, pixel_loss=None, perceptual_loss=None, discriminator=None, gan_loss=None,
+                 rgb_mean=(0.5, 0.5, 0.5), rgb_std=(0.5, 0.5, 0.5), train_cfg=None, test_cfg=None,
+                 pretrained=None, is_use_sharpened_gt_in_pixel=False, is_use_sharpened_gt_in_percep=False,
+                 is_use_sharpened_gt_in_gan=False, is_use_ema=True):
+        super().__init__(generator, pixel_loss if pixel_loss is not None else dict(type="L1Loss"),
+                         rgb_mean=rgb_mean, rgb_std=rgb_std, train_cfg=train_cfg, test_cfg=test_cfg,
+                         pretrained=pretrained)
+        self.perceptual_loss_cfg, self.discriminator_cfg, self.gan_loss_cfg = perceptual_loss, discriminator, gan_loss
+        self.is_use_sharpened_gt_in_pixel = is_use_sharpened_gt_in_pixel
+        self.is_use_sharpened_gt_in_percep = is_use_sharpened_gt_in_percep
+        self.is_use_sharpened_gt_in_gan = is_use_sharpened_gt_in_gan
+        self.is_use_ema = is_use_ema
+        self.generator_ema = copy.deepcopy(self.generator) if is_use_ema else None
+        self.register_buffer("step_counter", torch.zeros(1))
+        self.start_iter = train_cfg.get("start_iter", -1) if train_cfg is not None else -1
+
+    def _test_generator(self):
+        return self.generator_ema if self.is_use_ema else self.generator
+
+    def train_step(self, data_batch, optimizer):
+        raise NotImplementedError("GAN training of RealCiaoSR is out of scope for ciaosr_b200 (SURVEY.md 8f #4)")

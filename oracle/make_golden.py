@@ -97,6 +97,23 @@ def clip_case(name, c, hidden, h, w, scale, tile, overlap, seed=0):
          dict(lq=lq.numpy(), out=out.numpy()))
 
 
+def swinir_case(name, shapes, seed=0, **kw):
+    """The SwinIR trunk (gen_feature) of the reference generator, with the reference's state_dict
+    keys and shapes recorded so that checkpoint compatibility is pinned too."""
+    g = rh.build_reference_swinir_generator(**kw)
+    synth.fill_module(g, seed)
+    arrays, tags = {}, []
+    with torch.no_grad():
+        for (b, h, w) in shapes:
+            x = synth.synth_lr_image(b, h, w, seed)
+            tag = f"{b}x{h}x{w}"
+            arrays[f"x_{tag}"] = x.numpy()
+            arrays[f"feat_{tag}"] = g.gen_feature(x)[0].numpy()
+            tags.append(tag)
+    keys = {k: list(v.shape) for k, v in g.state_dict().items()}
+    save(name, dict(kind="swinir", seed=seed, tags=tags, cfg=kw, state_keys=keys), arrays)
+
+
 def save(name, meta, arrays):
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
@@ -124,6 +141,9 @@ def main():
     csattn_case("csattn_odd", 16, 2, 9, 11, seed=8)
     # tiled inference through the restorer
     clip_case("clip_small", 16, (32, 32), 40, 36, 2, 24, 8, seed=9)
+    # SwinIR trunk: window-multiple size (buffered shift mask), padded sizes (reflect pad + recomputed mask)
+    swinir_case("swinir_trunk", [(1, 8, 8), (2, 10, 13), (1, 16, 12)], seed=10,
+                embed_dim=24, depths=(2, 2), num_heads=(2, 2), window_size=4, img_size=8, mlp_ratio=2)
 
 
 if __name__ == "__main__":

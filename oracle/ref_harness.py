@@ -22,6 +22,10 @@ Stubbed names and the reference lines that import them:
                                                         basic_restorer.py:10-11
   mmedit.core.{tensor2img, psnr, ssim}                  basic_restorer.py:9
   thop.profile                                          ciaosr.py:15
+  timm.models.layers.{DropPath, to_2tuple, trunc_normal_}  swinir_net.py:11
+The reference's SwinIR also calls ``.cuda()`` on sub-modules inside its constructor
+(swinir_net.py:684,723,725); ``build_reference_swinir_generator`` neutralises ``nn.Module.cuda``
+for the duration of that constructor so the trunk can be built in the GPU-less container.
 
 ``/root/reference`` does not exist on the GPU box; everything that imports
 this module must be guarded by :func:`reference_available`.
@@ -185,6 +189,21 @@ def _install_stubs():
     thop = mod("thop")
     thop.profile = lambda *a, **k: (0, 0)
 
+    class _DropPath(nn.Module):                      # inference: identity
+        def __init__(self, drop_prob=None):
+            super().__init__()
+
+        def forward(self, x):
+            return x
+
+    timm = mod("timm")
+    tmodels = mod("timm.models")
+    tlayers = mod("timm.models.layers")
+    tlayers.DropPath = _DropPath
+    tlayers.to_2tuple = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    tlayers.trunc_normal_ = nn.init.trunc_normal_
+    timm.models, tmodels.layers = tmodels, tlayers
+
 
 _REF = None
 
@@ -214,6 +233,7 @@ def import_reference():
         mlp = importlib.import_module(
             "mmedited.models.components.refiners.mlp_refiner")
         restorer = importlib.import_module("mmedited.models.restorers.ciaosr")
+        swinir = importlib.import_module("mmedited.models.backbones.sr_backbones.swinir_net")
     finally:
         sys.path.remove(REFERENCE_ROOT)
         for name in [n for n in sys.modules if n == "mmedited" or n.startswith("mmedited.")]:
@@ -221,7 +241,7 @@ def import_reference():
         sys.modules.update(saved)
         importlib.invalidate_caches()
     assert net.__file__.startswith(REFERENCE_ROOT), net.__file__
-    _REF = types.SimpleNamespace(net=net, csnln=csnln, mlp=mlp,
+    _REF = types.SimpleNamespace(net=net, csnln=csnln, mlp=mlp, swinir=swinir,
                                  restorer=restorer, make_coord=make_coord)
     return _REF
 
@@ -247,4 +267,23 @@ def build_reference_generator(kind="edsr", mid_channels=64, hidden=(256, 256, 25
     gen = cls(encoder=enc, imnet_q=mlp_cfg(), imnet_k=mlp_cfg(), imnet_v=mlp_cfg(),
               local_size=local_size, feat_unfold=True, eval_bsize=eval_bsize,
               non_local_attn=non_local_attn, softmax_scale=softmax_scale)
+    return gen.eval()
+
+
+def build_reference_swinir_generator(embed_dim=24, depths=(2, 2), num_heads=(2, 2), window_size=4, img_size=8,
+                                     mlp_ratio=2, hidden=(16, 16), non_local_attn=False):
+    """The reference's LocalImplicitSRSWINIR over its own SwinIR, small, on the CPU."""
+    ref = import_reference()
+    mlp_cfg = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3, hidden_list=list(hidden))
+    enc = dict(type=ref.swinir.SwinIR, upscale=4, in_chans=3, img_size=img_size, window_size=window_size,
+               img_range=1., depths=list(depths), embed_dim=embed_dim, num_heads=list(num_heads),
+               mlp_ratio=mlp_ratio, upsampler="pixelshuffle", resi_connection="1conv")
+    saved = nn.Module.cuda
+    nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        gen = ref.net.LocalImplicitSRSWINIR(window_size=window_size, encoder=enc, imnet_q=mlp_cfg(),
+                                            imnet_k=mlp_cfg(), imnet_v=mlp_cfg(), feat_unfold=True,
+                                            eval_bsize=None, non_local_attn=non_local_attn)
+    finally:
+        nn.Module.cuda = saved
     return gen.eval()
