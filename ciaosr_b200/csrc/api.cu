@@ -177,7 +177,7 @@ static int cs_engine(const PlanLayout& L, int engine, bool* use_tc) {
   CIAOSR_REQUIRE(engine >= CIAOSR_ENGINE_AUTO && engine <= CIAOSR_ENGINE_TCGEN05, CIAOSR_E_INVALID,
                  "unknown engine %d", engine);
   CIAOSR_REQUIRE(engine != CIAOSR_ENGINE_TCGEN05 || cs_attn_tc_ok(L), CIAOSR_E_INVALID,
-                 "tcgen05 cross-scale attention needs C %% 8 == 0");
+                 "tcgen05 cross-scale attention needs C %% 4 == 0");
   *use_tc = engine != CIAOSR_ENGINE_SIMT && cs_attn_tc_ok(L);
   return CIAOSR_OK;
 }

@@ -117,12 +117,12 @@ __global__ void csa_fold_batch_kernel(const float* __restrict__ o, float* __rest
 }
 
 // ---- operand sources for the per-image blobs ----------------------------------------------------
-struct KhatSrc {            // B[n = l, k = t*Ch + c] = R_pad[l + tap t, c] / max(|patch l|, eps)
-  const float* r; const float* nrm; int Hl, Wl, Ch, img0;
+struct KhatSrc {            // B[n = l, k = t*Chp + c] = R_pad[l + tap t, c] / max(|patch l|, eps); 0 for c >= Ch
+  const float* r; const float* nrm; int Hl, Wl, Ch, Chp, img0;
   __device__ __forceinline__ float operator()(int image, int n, int k) const {
-    const int img = img0 + image, t = k / Ch, c = k % Ch;
+    const int img = img0 + image, t = k / Chp, c = k % Chp;
     const int y = n / Wl + t / 3 - 1, x = n % Wl + t % 3 - 1;
-    if (y < 0 || y >= Hl || x < 0 || x >= Wl) return 0.0f;
+    if (c >= Ch || y < 0 || y >= Hl || x < 0 || x >= Wl) return 0.0f;
     return __fdiv_rn(r[(((long long)img * Hl + y) * Wl + x) * Ch + c], nrm[(long long)img * Hl * Wl + n]);
   }
 };
@@ -141,7 +141,7 @@ struct DownSrc {            // B[n = co, k = (u*3+v)*C + ci] = down_wt[k, co]
 };
 
 // ---- A generators / epilogues ----------------------------------------------------------------------
-struct QPatchGen {          // rows = (img, y, x) of the group; k = t*Ch + c, Ch % 4 == 0
+struct QPatchGen {          // rows = (img, y, x) of the group; k = t*Ch + c; Ch = padded row stride of Mi, % 4 == 0
   const float* mi; int Hp, Wp, Ch, K; long long pix0;
   struct Row { int y, x; long long pix; };
   __device__ __forceinline__ Row row(long long m) const {
@@ -150,17 +150,27 @@ struct QPatchGen {          // rows = (img, y, x) of the group; k = t*Ch + c, Ch
     return Row{r / Wp, r % Wp, p};
   }
   __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+    const float* self = mi + r.pix * Ch;       // loads are unconditional (masked afterwards): all 8 in flight together
+    const float* src[8];
+    bool ok[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      src[g] = self; ok[g] = false;
       if (k < K) {
         const int t = k / Ch, c = k - t * Ch;
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        if (r.y + dy >= 0 && r.y + dy < Hp && r.x + dx >= 0 && r.x + dx < Wp)
-          q = __ldg(reinterpret_cast<const float4*>(mi + (r.pix + dy * Wp + dx) * Ch + c));
+        const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
+        ok[g] = r.y + dy >= 0 && r.y + dy < Hp && r.x + dx >= 0 && r.x + dx < Wp;
+        if (ok[g]) src[g] = self + (dy * Wp + dx) * Ch + c;
       }
-      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+    float4 q[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
+      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
     }
   }
 };
@@ -216,17 +226,28 @@ struct DownGen {            // rows = cropped output pixels (img, y, x); k = (u*
     return Row{hw / W, hw % W, hw, m / ((long long)H * W)};
   }
   __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+    const float* centre = cv + (((r.img * H2) + 2 * r.y) * W2 + 2 * r.x) * C;    // always inside the canvas
+    const float* src[8];
+    bool ok[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      src[g] = centre; ok[g] = false;
       if (k < K) {
         const int uv = k / C, ci = k - uv * C;
-        const int Y = 2 * r.y - 1 + uv / 3, X = 2 * r.x - 1 + uv % 3;
-        if (Y >= 0 && Y < H2 && X >= 0 && X < W2)
-          q = __ldg(reinterpret_cast<const float4*>(cv + (((r.img * H2) + Y) * W2 + X) * C + ci));
+        const int u = uv / 3, w = uv - u * 3;
+        const int Y = 2 * r.y - 1 + u, X = 2 * r.x - 1 + w;
+        ok[g] = Y >= 0 && Y < H2 && X >= 0 && X < W2;
+        if (ok[g]) src[g] = centre + ((u - 1) * W2 + (w - 1)) * C + ci;
       }
-      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+    float4 q[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
+      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
     }
   }
 };
@@ -249,6 +270,7 @@ struct DownEpi {            // (acc + b) / 6 -> NHWC slice and / or NCHW
 // ---- host orchestration ------------------------------------------------------------------------------
 struct CsaTcSizes {
   int Hp, Wp, Hl, Wl, L, ldS, HWp, group;      // group = images processed together
+  int Chp;
   int kq_slabs, kq_units, vt_slabs, vt_units, dn_slabs, dn_units;
 };
 static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
@@ -256,7 +278,8 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   s.Hp = H + (H & 1); s.Wp = W + (W & 1);
   s.Hl = s.Hp / 2; s.Wl = s.Wp / 2; s.L = s.Hl * s.Wl; s.ldS = (s.L + 3) / 4 * 4;
   s.HWp = s.Hp * s.Wp;
-  s.kq_slabs = (9 * (C / 2) + KSLAB - 1) / KSLAB; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
+  s.Chp = (C / 2 + 3) / 4 * 4;                 // query-embedding channels, zero padded to the float4 gathers
+  s.kq_slabs = (9 * s.Chp + KSLAB - 1) / KSLAB; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
   s.vt_slabs = (s.L + KSLAB - 1) / KSLAB; s.vt_units = (36 * C + UNIT_N - 1) / UNIT_N;
   s.dn_slabs = (9 * C + KSLAB - 1) / KSLAB; s.dn_units = (C + UNIT_N - 1) / UNIT_N;
   // images per pass: tiles must not straddle images, and the score tensor stays <= 1 GiB
@@ -268,14 +291,14 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   return s;
 }
 
-bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 8 == 0; }
+bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
 struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; uint8_t *kblob, *vblob, *dblob; };
 static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s, int B) {
   CsaTcBufs b;
   const int C = L.C, Ch = C / 2, g = s.group;
   b.E = a.take<float>((size_t)B * s.HWp * C);
-  b.Mi = a.take<float>((size_t)B * s.HWp * Ch);
+  b.Mi = a.take<float>((size_t)B * s.HWp * s.Chp);
   b.R = a.take<float>((size_t)B * s.L * Ch);
   b.nrm = a.take<float>((size_t)B * s.L);
   b.S = a.take<float>((size_t)g * s.HWp * s.ldS);
@@ -309,8 +332,9 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
   PadFeatBatchA pa{featT, H, W, s.Hp, s.Wp, C};
   if ((rc = gemm_simt(B * s.HWp, C, C, pa, RowMajorB{plan + L.as_wt, C},
                       EpiPrelu{b.E, C, plan + L.as_b, scal + 2}, st))) return rc;
+  if (s.Chp != Ch) CIAOSR_CUDA_OK(cudaMemsetAsync(b.Mi, 0, (size_t)B * s.HWp * s.Chp * sizeof(float), st));
   if ((rc = gemm_simt(B * s.HWp, Ch, C, pa, RowMajorB{plan + L.m1_wt, Ch},
-                      EpiPrelu{b.Mi, Ch, plan + L.m1_b, scal + 0}, st))) return rc;
+                      EpiPrelu{b.Mi, s.Chp, plan + L.m1_b, scal + 0}, st))) return rc;
   if ((rc = gemm_simt(B * s.L, Ch, C, PoolFeatBatchA{featT, H, W, s.Hl, s.Wl, C}, RowMajorB{plan + L.m2_wt, Ch},
                       EpiPrelu{b.R, Ch, plan + L.m2_b, scal + 1}, st))) return rc;
   CIAOSR_LAUNCH(csa_knorm_batch_kernel, B * s.L, 128, 0, st, b.R, b.nrm, s.Hl, s.Wl, Ch, scal);
@@ -321,10 +345,10 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
   for (int i0 = 0; i0 < B; i0 += s.group) {
     const int g = min(s.group, B - i0);
     const long long rows = (long long)g * s.HWp;
-    if ((rc = tc_pack_operand(b.kblob, g, s.L, 9 * Ch, kstride, KhatSrc{b.R, b.nrm, s.Hl, s.Wl, Ch, i0}, st)))
+    if ((rc = tc_pack_operand(b.kblob, g, s.L, 9 * s.Chp, kstride, KhatSrc{b.R, b.nrm, s.Hl, s.Wl, Ch, s.Chp, i0}, st)))
       return rc;
     if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob,
-                      QPatchGen{b.Mi, s.Hp, s.Wp, Ch, 9 * Ch, (long long)i0 * s.HWp},
+                      QPatchGen{b.Mi, s.Hp, s.Wp, s.Chp, 9 * s.Chp, (long long)i0 * s.HWp},
                       ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st))) return rc;
     CIAOSR_LAUNCH(softmax_rows_ld_kernel, cdiv(rows, 8), 256, 0, st, b.S, rows, s.L, s.ldS);
     if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))

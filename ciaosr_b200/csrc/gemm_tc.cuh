@@ -10,6 +10,7 @@
 // 256 columns that fit the four operand slots, so slabs stream through them under A_FREE).
 // Same pipeline, barriers and bf16x3 arithmetic as head_tc.cu (tc_pipeline.cuh).
 #pragma once
+#include <type_traits>
 #include "tc_pipeline.cuh"
 
 namespace ciaosr {
@@ -24,15 +25,29 @@ struct GemmShape {
 
 // AGen:  struct Row;  __device__ Row row(long long m) const;
 //        __device__ void fill(Row&, long long m, int k0, float (&v)[32]) const;     (k0 % 32 == 0)
+//        optional: static constexpr bool kCombine = true;  __device__ float& partial(Row&) const;
+//                  (a per-row scalar accumulated by fill(); the two threads of a row hold partial sums that are
+//                   added through smem before the epilogue sees the row)
 // Epi:   __device__ void store(const typename AGen::Row&, long long m, int n0, const float (&v)[32]) const;
-constexpr int TC_THREADS = 256;      // 4 control warps + 128 row threads
+//
+// Threads: 4 control warps + 8 row warps.  Two threads serve each row: thread (half h, lane-quarter q, lane l)
+// <-> row 32 q + l, columns [32 h, 32 h + 32) of every 64-column operand slab and the 32-column accumulator
+// chunks 2 j + h (warps 4-7 are h = 0, warps 8-11 are h = 1; a warp may only touch TMEM lanes 32 (warp % 4) ..+31).
+// Two warps per SM sub-partition overlap one thread's gather latency with the other's conversion work.
+constexpr int TC_THREADS = 384;
+constexpr int TC_NEPI = 256;
+
+template <class AGen, class = void>
+struct agen_combines : std::false_type {};
+template <class AGen>
+struct agen_combines<AGen, std::enable_if_t<AGen::kCombine>> : std::true_type {};
 
 template <class AGen, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcShared s = tc_carve(smem);
-  const uint32_t tmem_base = tc_prologue<1, 128>(s, smem);
+  const uint32_t tmem_base = tc_prologue<1, TC_NEPI>(s, smem);
   const int warp = threadIdx.x >> 5;
   const int m_tiles = (int)((g.M + ROWS - 1) / ROWS);
   const int n_chunks = (g.nunits + 1) / 2;
@@ -55,7 +70,8 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
       mma_job<1>(s, tmem_base, m, g.kslabs, min(2, g.nunits - 2 * nc), true);
     }
   } else if (warp >= 4) {
-    const int row = threadIdx.x - EPI_T0;
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + (threadIdx.x & 31);
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     EpiState e{0, 0xFu, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -67,27 +83,30 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
 #pragma unroll 1
       for (int sl = 0; sl < g.kslabs; ++sl) {
         const int slot = sl & 3;
-        slab_begin(s, e, slot, true);
+        float v[32];
+        if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
+        else {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
-          else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-          }
-          a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
         }
+        slab_begin(s, e, slot, true);
+        a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
         slab_done(s, slot);
+      }
+      if constexpr (agen_combines<AGen>::value) {
+        s.xchg[half * ROWS + row] = agen.partial(rs);
+        epi_sync<TC_NEPI>();
+        agen.partial(rs) = s.xchg[row] + s.xchg[ROWS + row];
       }
       const uint32_t d = epi_wait_d(s, e, units);
 #pragma unroll 1
-      for (int cc = 0; cc < units * 4; ++cc) {
+      for (int cc = half; cc < units * 4; cc += 2) {
         float v[32];
         tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
         if (valid) epi.store(rs, m, nc * 256 + cc * 32, v);
       }
       epi_release_d(s, e);
+      if constexpr (agen_combines<AGen>::value) epi_sync<TC_NEPI>();     // xchg is rewritten by the next job
     }
   }
   tc_teardown<1>(tmem_base);

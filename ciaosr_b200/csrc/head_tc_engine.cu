@@ -173,6 +173,9 @@ int tc_pack(const ciaosr_head_desc* d, const PlanLayout& L, float* plan, cudaStr
 // =====================================================================================================
 // LR-resolution precompute on the tensor cores (replaces run_lr_precompute's CUDA-core GEMMs)
 // =====================================================================================================
+// Both generators gather 8 float4 per 32-column chunk.  All addresses are formed first and every load is
+// unconditional (out-of-image taps read the row's own pixel and are masked afterwards), so the 8 (or 16)
+// loads of a chunk are in flight together instead of one L2 round trip per branch.
 struct UnfoldGen {       // A[pix, kp] = tap-major 3x3 unfold of the NHWC feature (+ non-local channels)
   const float* f; const float* nl; int H, W, C, Cn, K;
   struct Row { int y, x; };
@@ -181,25 +184,38 @@ struct UnfoldGen {       // A[pix, kp] = tap-major 3x3 unfold of the NHWC featur
     return Row{hw / W, hw % W};
   }
   __device__ __forceinline__ void fill(Row& r, long long m, int k0, float (&v)[32]) const {
+    const float* src[8];
+    bool ok[8];
+    const float* self = f + m * C;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      src[g] = self; ok[g] = false;
       if (k < 9 * C) {
         const int t = k / C, ch = k - t * C;
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        if (r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W)
-          q = __ldg(reinterpret_cast<const float4*>(f + (m + dy * W + dx) * C + ch));
+        const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
+        ok[g] = r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W;
+        if (ok[g]) src[g] = self + (dy * W + dx) * C + ch;
       } else if (k < K) {
-        q = __ldg(reinterpret_cast<const float4*>(nl + m * Cn + (k - 9 * C)));
+        ok[g] = true;
+        src[g] = nl + m * Cn + (k - 9 * C);
       }
-      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+    }
+    float4 q[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
+      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
     }
   }
 };
 struct PairProdGen {     // A[pix*9 + d, kp] = U[pix, kp] * U[pix + d, kp];  also c0 = sum_kp A * b5[kp]
+  static constexpr bool kCombine = true;
   const float* f; const float* fin; int H, W, C, ldfin;     // fin[kp * ldfin + 256] = permuted last-layer bias
   struct Row { int y, x, dy, dx; long long pix; bool ok; float c0; };
+  __device__ __forceinline__ float& partial(Row& r) const { return r.c0; }
   __device__ __forceinline__ Row row(long long m) const {
     Row r;
     r.pix = m / 9;
@@ -210,27 +226,45 @@ struct PairProdGen {     // A[pix*9 + d, kp] = U[pix, kp] * U[pix + d, kp];  als
     return r;
   }
   __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
+    const float* self = f + r.pix * C;
+    const int doff = r.ok ? (r.dy * W + r.dx) * C : 0;
+    const float* src[8];
+    const float* bsrc[8];
+    bool ok[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      src[g] = self; ok[g] = false; bsrc[g] = fin + HID;
       if (r.ok && k < 9 * C) {
         const int t = k / C, ch = k - t * C;
-        const int ty = t / 3 - 1, tx = t % 3 - 1;
+        const int ty = t / 3 - 1, tx = t - (ty + 1) * 3 - 1;
         const int ay = r.y + ty, ax = r.x + tx, by = ay + r.dy, bx = ax + r.dx;
-        if (ay >= 0 && ay < H && ax >= 0 && ax < W && by >= 0 && by < H && bx >= 0 && bx < W) {
-          const float* pa = f + (r.pix + ty * W + tx) * C + ch;
-          const float4 a = __ldg(reinterpret_cast<const float4*>(pa));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(pa + (r.dy * W + r.dx) * C));
-          q = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-          r.c0 = fmaf(q.x, __ldg(fin + (long long)k * ldfin + HID), r.c0);
-          r.c0 = fmaf(q.y, __ldg(fin + (long long)(k + 1) * ldfin + HID), r.c0);
-          r.c0 = fmaf(q.z, __ldg(fin + (long long)(k + 2) * ldfin + HID), r.c0);
-          r.c0 = fmaf(q.w, __ldg(fin + (long long)(k + 3) * ldfin + HID), r.c0);
-        }
+        ok[g] = ay >= 0 && ay < H && ax >= 0 && ax < W && by >= 0 && by < H && bx >= 0 && bx < W;
+        if (ok[g]) { src[g] = self + (ty * W + tx) * C + ch; bsrc[g] = fin + (long long)k * ldfin + HID; }
       }
-      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
     }
+    float4 a[8], b[8];
+    float w5[8][4];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      a[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+      b[g] = __ldg(reinterpret_cast<const float4*>(src[g] + (ok[g] ? doff : 0)));
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w5[g][i] = __ldg(bsrc[g] + (ok[g] ? (long long)i * ldfin : 0));
+    }
+    float c0 = 0.0f, c1 = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float m0 = ok[g] ? a[g].x * b[g].x : 0.f, m1 = ok[g] ? a[g].y * b[g].y : 0.f;
+      const float m2 = ok[g] ? a[g].z * b[g].z : 0.f, m3 = ok[g] ? a[g].w * b[g].w : 0.f;
+      v[4 * g] = m0; v[4 * g + 1] = m1; v[4 * g + 2] = m2; v[4 * g + 3] = m3;
+      c0 = fmaf(m0, w5[g][0], c0); c1 = fmaf(m1, w5[g][1], c1);
+      c0 = fmaf(m2, w5[g][2], c0); c1 = fmaf(m3, w5[g][3], c1);
+    }
+    r.c0 += c0 + c1;
   }
 };
 template <class Row>

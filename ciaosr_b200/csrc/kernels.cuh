@@ -12,7 +12,7 @@ int run_cs_attn(const PlanLayout& L, const float* plan, const float* featT, int 
                 float* out_nhwc, int ldo, float* out_nchw, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 
-// cs_attn_tc.cu (tensor-core path; needs C % 8 == 0)
+// cs_attn_tc.cu (tensor-core path; needs C % 4 == 0)
 bool cs_attn_tc_ok(const PlanLayout& L);
 size_t cs_attn_tc_workspace(const PlanLayout& L, int B, int H, int W);
 int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, int B, int H, int W,

@@ -136,8 +136,13 @@ def main():
               random_q=300)
     head_case("head_c64_nonl0", 64, (256, 256, 256, 256), 1, 10, 12, [3], eval_bsize=None,
               non_local=False, seed=6)
+    # SwinIR-sized head (configs 001-swinir / 002: C = 180, 9C is not a multiple of 64 or 128)
+    head_case("head_c180", 180, (256, 256, 256, 256), 1, 8, 10, [3], eval_bsize=1000, seed=12)
+    head_case("head_c180_nonl0", 180, (256, 256, 256, 256), 1, 6, 8, [4], eval_bsize=None,
+              non_local=False, seed=13)
     # cross-scale attention alone
     csattn_case("csattn_c64", 64, 1, 24, 20, seed=7)
+    csattn_case("csattn_c180", 180, 1, 12, 16, seed=14)
     csattn_case("csattn_odd", 16, 2, 9, 11, seed=8)
     # tiled inference through the restorer
     clip_case("clip_small", 16, (32, 32), 40, 36, 2, 24, 8, seed=9)

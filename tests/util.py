@@ -12,8 +12,8 @@ from ciaosr_b200.generators import LocalImplicitSREDSR
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 HEAD_CASES = ["head_small", "head_frac", "head_ls1", "head_ls3", "head_nonl0", "head_c64",
-              "head_c64_nonl0"]
-CSATTN_CASES = ["csattn_c64", "csattn_odd"]
+              "head_c64_nonl0", "head_c180", "head_c180_nonl0"]
+CSATTN_CASES = ["csattn_c64", "csattn_odd", "csattn_c180"]
 
 
 def load_case(name):
