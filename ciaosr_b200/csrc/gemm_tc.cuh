@@ -148,15 +148,15 @@ __global__ void tc_pack_operand_kernel(uint8_t* __restrict__ dst, int N, int K, 
   const int ug = rest % nunits, sl = rest / nunits;
   const int n = ug * UNIT_N + n_in, k = sl * KSLAB + k_in;
   const float w = (n < N && k < K) ? src(image, n, k) : 0.0f;
-  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  split_t hi, lo;
+  split_scalar(w, hi, lo);
   const int nc = ug / 2, u = ug % 2;
   const int units = min(2, nunits - 2 * nc);
   const size_t unit_index = (size_t)nc * 2 * kslabs + (size_t)sl * units + u;
   uint8_t* ub = dst + image * image_stride + unit_index * UNIT_BYTES;
   const uint32_t off = sw128_offset(n_in, k_in);
-  *reinterpret_cast<__nv_bfloat16*>(ub + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(ub + SLAB_BYTES + off) = lo;
+  *reinterpret_cast<split_t*>(ub + off) = hi;
+  *reinterpret_cast<split_t*>(ub + SLAB_BYTES + off) = lo;
 }
 
 inline size_t tc_operand_blob_bytes(int kslabs, int nunits) { return (size_t)kslabs * nunits * UNIT_BYTES; }

@@ -98,12 +98,12 @@ __global__ void tc_pack_job_kernel(uint8_t* __restrict__ dst, const float* __res
     const int ks = (perm_cols && k < Dk) ? (k % C) * 9 + k / C : k;
     w = trans ? W[(long long)ks * ld + ns] : W[(long long)ns * ld + ks];   // trans: W is [K, N]
   }
-  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  split_t hi, lo;
+  split_scalar(w, hi, lo);
   uint8_t* ub = dst + (size_t)unit * UNIT_BYTES;
   const uint32_t off = sw128_offset(n_in, k_in);
-  *reinterpret_cast<__nv_bfloat16*>(ub + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(ub + SLAB_BYTES + off) = lo;
+  *reinterpret_cast<split_t*>(ub + off) = hi;
+  *reinterpret_cast<split_t*>(ub + SLAB_BYTES + off) = lo;
 }
 
 __global__ void tc_pack_consts_kernel(float* __restrict__ pc, float* __restrict__ bv5p, float* __restrict__ qc,

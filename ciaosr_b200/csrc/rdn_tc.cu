@@ -45,7 +45,7 @@ constexpr int CW_A_READY = 0, CW_A_FREE = 4, CW_W_FULL = 8, CW_W_EMPTY = 16, CW_
               CW_NBARS = 28;
 constexpr int CW_FIXED_BYTES = 32 * CW_T_LD * 4 + 64 * 4 + CW_NBARS * 8 + 16;
 
-struct ConvDst { __nv_bfloat16* hi; __nv_bfloat16* lo; int ld; int choff; };
+struct ConvDst { split_t* hi; split_t* lo; int ld; int choff; };
 
 struct ConvParams {
   int B, H, W, tiles_x, tiles_y, n_tiles;
@@ -144,7 +144,7 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
     }
   } else if (warp == 1) {
     // ---- UMMA issuer ----
-    const uint32_t idesc = make_idesc_bf16(ROWS, 128);
+    const uint32_t idesc = make_idesc_split(ROWS, 128);
     const uint32_t bhw = (uint32_t)((P.box_x * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
     uint32_t acnt = 0, wcnt = 0, job = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++job) {
@@ -304,7 +304,7 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
 // chunk-major: [K-slab][16-byte chunk j = k / 8][row][k % 8], rows = [W_hi (64); W_lo (64)], so that the 32 rows
 // a stager warp loads with one instruction are 512 contiguous bytes
 constexpr int WSLAB_BYTES = 128 * 64 * 2;
-__global__ void rdn_pack_rows_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ w, int Cin, int ntaps) {
+__global__ void rdn_pack_rows_kernel(split_t* __restrict__ dst, const float* __restrict__ w, int Cin, int ntaps) {
   const int cblocks = Cin / 64;
   const long long total = (long long)cblocks * ntaps * 64 * 64;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -313,9 +313,9 @@ __global__ void rdn_pack_rows_kernel(__nv_bfloat16* __restrict__ dst, const floa
   const int sl = (int)(i / 4096);
   const int cb = sl / ntaps, tap = sl % ntaps;
   const float v = w[((long long)n * Cin + cb * 64 + k) * ntaps + tap];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-  __nv_bfloat16* ub = dst + (size_t)sl * 128 * 64;
+  split_t hi, lo;
+  split_scalar(v, hi, lo);
+  split_t* ub = dst + (size_t)sl * 128 * 64;
   ub[((k >> 3) * 128 + n) * 8 + (k & 7)] = hi;
   ub[((k >> 3) * 128 + 64 + n) * 8 + (k & 7)] = lo;
 }
@@ -347,7 +347,7 @@ struct Sfe1Src {          // B[n, k] = w[n*27 + k]
   __device__ __forceinline__ float operator()(int, int n, int k) const { return w[n * 27 + k]; }
 };
 struct Sfe1Epi {          // + bias -> NHWC bf16 hi/lo + fp32
-  __nv_bfloat16* hi; __nv_bfloat16* lo; float* out32; const float* bias;
+  split_t* hi; split_t* lo; float* out32; const float* bias;
   __device__ __forceinline__ void store(const Sfe1Gen::Row&, long long g, int n0, const float (&v)[32]) const {
     if (n0 >= 64) return;
     float t[32];
@@ -445,7 +445,7 @@ static int make_map(CUtensorMap* m, void* base, int B, int H, int W, int channel
 
 struct RdnWs {
   long long M;         // B*H*W pixels
-  __nv_bfloat16 *f1h, *f1l, *rbh[2], *rbl[2], *gfh, *gfl, *g1h, *g1l;
+  split_t *f1h, *f1l, *rbh[2], *rbl[2], *gfh, *gfl, *g1h, *g1l;
   float *f1_32, *xr[2];
 };
 static RdnWs rdn_carve(Arena& a, const ciaosr_rdn_desc* d, int B, int H, int W) {
@@ -453,17 +453,17 @@ static RdnWs rdn_carve(Arena& a, const ciaosr_rdn_desc* d, int B, int H, int W) 
   w.M = (long long)B * H * W;
   const size_t n = (size_t)w.M;
   const int cb = 64 * (1 + d->num_layers);
-  w.f1h = a.take<__nv_bfloat16>(n * 64); w.f1l = a.take<__nv_bfloat16>(n * 64);
-  for (int i = 0; i < 2; ++i) { w.rbh[i] = a.take<__nv_bfloat16>(n * cb); w.rbl[i] = a.take<__nv_bfloat16>(n * cb); }
-  w.gfh = a.take<__nv_bfloat16>(n * 64 * d->num_blocks); w.gfl = a.take<__nv_bfloat16>(n * 64 * d->num_blocks);
-  w.g1h = a.take<__nv_bfloat16>(n * 64); w.g1l = a.take<__nv_bfloat16>(n * 64);
+  w.f1h = a.take<split_t>(n * 64); w.f1l = a.take<split_t>(n * 64);
+  for (int i = 0; i < 2; ++i) { w.rbh[i] = a.take<split_t>(n * cb); w.rbl[i] = a.take<split_t>(n * cb); }
+  w.gfh = a.take<split_t>(n * 64 * d->num_blocks); w.gfl = a.take<split_t>(n * 64 * d->num_blocks);
+  w.g1h = a.take<split_t>(n * 64); w.g1l = a.take<split_t>(n * 64);
   w.f1_32 = a.take<float>(n * 64);
   for (int i = 0; i < 2; ++i) w.xr[i] = a.take<float>(n * 64);
   return w;
 }
 
 struct MapPair { CUtensorMap m[2][2]; };     // [0] 3x3 box (10 x 18), [1] 1x1 box (8 x 16); [hi, lo]
-static int make_maps(MapPair* mp, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int H, int W, int channels) {
+static int make_maps(MapPair* mp, split_t* hi, split_t* lo, int B, int H, int W, int channels) {
   int rc;
   if ((rc = make_map(&mp->m[0][0], hi, B, H, W, channels, TILE_X + 2, TILE_Y + 2)) ||
       (rc = make_map(&mp->m[0][1], lo, B, H, W, channels, TILE_X + 2, TILE_Y + 2)) ||
@@ -522,7 +522,7 @@ int ciaosr_rdn_plan_init(const ciaosr_rdn_desc* d, void* plan, size_t plan_bytes
   int bi = 0;
   auto pack = [&](size_t off, const float* w, const float* b, int Cin, int ntaps) -> int {
     const long long total = (long long)(Cin / 64) * ntaps * 4096;
-    CIAOSR_LAUNCH(rdn_pack_rows_kernel, cdiv(total, 256), 256, 0, st, reinterpret_cast<__nv_bfloat16*>(p + off), w,
+    CIAOSR_LAUNCH(rdn_pack_rows_kernel, cdiv(total, 256), 256, 0, st, reinterpret_cast<split_t*>(p + off), w,
                   Cin, ntaps);
     CIAOSR_LAUNCH(rdn_copy64_kernel, 1, 64, 0, st, bias + 64 * bi, b);
     ++bi;

@@ -156,7 +156,7 @@ template <int CL>
 __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, MmaState& m, int nslabs,
                                         int units, bool a_new) {
   const bool leader = (threadIdx.x & 31) == 0;
-  const uint32_t idesc = make_idesc_bf16(ROWS, UNIT_N * units);
+  const uint32_t idesc = make_idesc_split(ROWS, UNIT_N * units);
   const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
   mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
   tc_fence_after();
@@ -239,7 +239,7 @@ template <int CL>
 __device__ __forceinline__ void mma_job_q(const TcShared& s, uint32_t tmem_base, MmaState& m, uint32_t& stage,
                                           int nslabs, int units, bool a_new) {
   const bool leader = (threadIdx.x & 31) == 0;
-  const uint32_t idesc = make_idesc_bf16(ROWS, UNIT_N);
+  const uint32_t idesc = make_idesc_split(ROWS, UNIT_N);
   const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
   mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
   tc_fence_after();
