@@ -209,13 +209,24 @@ struct ProbGen {            // A = P rows (fp32, ld % 4 == 0), K = L
     }
   }
 };
-struct OutEpi {             // O[m, n] = acc, n < N (N % 4 == 0)
+struct OutEpi {             // O[m, n] = acc, n < N (N % 4 == 0); accumulate: O += acc (K chunks, see gemm_tc.cuh)
   float* o; int N;
   __device__ __forceinline__ void store(const ProbGen::Row&, long long m, int n0, const float (&v)[32]) const {
     float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (n0 + 4 * j < N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  __device__ __forceinline__ void accumulate(const ProbGen::Row&, long long m, int n0, const float (&v)[32]) const {
+    float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
+    float4 old[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + 4 * j < N) old[j] = dst[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + 4 * j < N)
+        dst[j] = make_float4(old[j].x + v[4 * j], old[j].y + v[4 * j + 1], old[j].z + v[4 * j + 2], old[j].w + v[4 * j + 3]);
   }
 };
 struct DownGen {            // rows = cropped output pixels (img, y, x); k = (u*3+v)*C + ci
@@ -291,6 +302,8 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   return s;
 }
 
+constexpr int CSA_KCHUNK = 16;     // P.V accumulates 1024 keys per TMEM pass; the passes are summed in fp32 (gemm_tc.cuh)
+
 bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
 struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; uint8_t *kblob, *vblob, *dblob; };
@@ -353,7 +366,7 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     CIAOSR_LAUNCH(softmax_rows_ld_kernel, cdiv(rows, 8), 256, 0, st, b.S, rows, s.L, s.ldS);
     if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
       return rc;
-    if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride}, b.vblob,
+    if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, CSA_KCHUNK}, b.vblob,
                       ProbGen{b.S, s.L, s.ldS}, OutEpi{b.O, 36 * C}, st))) return rc;
     const long long ctot = (long long)g * 4 * s.HWp * C;
     CIAOSR_LAUNCH(csa_fold_batch_kernel, cdiv(ctot, 256), 256, 0, st, b.O, b.cv, s.Hp, s.Wp, C, ctot);

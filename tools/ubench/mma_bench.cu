@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int nd, long l
   const bool leader = CG == 1 || cluster_ctarank() == 0;
   long long dt = 0;
   if (threadIdx.x == 0 && leader) {
-    const uint32_t idesc = make_idesc_bf16(128 * CG, N);
+    const uint32_t idesc = make_idesc_split(128 * CG, N);
     const uint32_t sb = smem_u32(smem);
     const long long t0 = clock64();
     const uint32_t a0 = ATMEM ? tb + 256 : dlo(sb), b0 = dlo(sb + 65536);

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256, 1) bench(int mode, int iters, const uint4
   const uint32_t tb = slot;
   const uint32_t sb = smem_u32(smem);
   if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, 256);
+    const uint32_t idesc = make_idesc_split(128, 256);
     const uint32_t a0 = dlo(sb), b0 = dlo(sb + 65536);
     const long long t0 = clock64();
     for (int i = 0; i < iters; i += 16) {
