@@ -302,7 +302,17 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   return s;
 }
 
-constexpr int CSA_KCHUNK = 16;     // P.V accumulates 1024 keys per TMEM pass; the passes are summed in fp32 (gemm_tc.cuh)
+// P.V accumulates 3072 keys per TMEM pass; the passes are summed in fp32 (gemm_tc.cuh).  Measured on a 192x192
+// tile (L = 9216 keys, C = 64; max-abs vs the fp32 engine / time): one pass 5.7e-5 / 8.4 ms, 48 slabs 4.0e-5 /
+// 8.9 ms, 16 slabs 3.1e-5 / 10.6 ms.  CIAOSR_CSA_KCHUNK overrides the slabs per pass (0 = one pass).
+static int csa_kchunk() {
+  static int kc = -1;
+  if (kc < 0) {
+    const char* e = getenv("CIAOSR_CSA_KCHUNK");
+    kc = e ? atoi(e) / 4 * 4 : 48;
+  }
+  return kc;
+}
 
 bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
@@ -366,7 +376,7 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     CIAOSR_LAUNCH(softmax_rows_ld_kernel, cdiv(rows, 8), 256, 0, st, b.S, rows, s.L, s.ldS);
     if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
       return rc;
-    if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, CSA_KCHUNK}, b.vblob,
+    if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, csa_kchunk()}, b.vblob,
                       ProbGen{b.S, s.L, s.ldS}, OutEpi{b.O, 36 * C}, st))) return rc;
     const long long ctot = (long long)g * 4 * s.HWp * C;
     CIAOSR_LAUNCH(csa_fold_batch_kernel, cdiv(ctot, 256), 256, 0, st, b.O, b.cv, s.Hp, s.Wp, C, ctot);

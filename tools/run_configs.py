@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--configs", default="3,4,5")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--stages", type=int, default=1, help="add per-stage times of one eager pass (1 GPU)")
     ap.add_argument("--check-crop", type=int, default=0,
                     help="tiled cases: run the fp32-engine comparison on a crop of this many LR rows/cols "
                          "(0 = 2x2 tiles worth); the timed run is always the full frame")
@@ -185,6 +186,24 @@ def main():
                     tiles=(len(m.tile_origins(h, min(test_cfg["tile"], h, w), test_cfg["tile_overlap"])) *
                            len(m.tile_origins(w, min(test_cfg["tile"], h, w), test_cfg["tile_overlap"]))
                            if test_cfg.get("tile") else 1))
+        if args.stages and world == 1:
+            # one eager pass with the library's per-stage CUDA events; "encoder+glue" is the remainder
+            from ciaosr_b200 import native
+            gen.cuda_graph = False
+            run()
+            torch.cuda.synchronize()
+            native.profile_read()
+            native.profile_enable(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            native.profile_enable(False)
+            st = {k: round(v[0], 3) for k, v in native.profile_read().items() if v[1]}
+            st["encoder+glue (eager)"] = round(e0.elapsed_time(e1) - sum(st.values()), 3)
+            line["stage_ms_per_frame"] = st
+            gen.cuda_graph = True
         if args.check and rank == 0 and world == 1:
             # product path vs the fp32 CUDA-core engine (+ PyTorch fp32 encoder) on the same input
             if test_cfg.get("tile"):
