@@ -91,7 +91,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -140,6 +140,15 @@ def peaks():
         return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/summarize_ncu.py from the same workload)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
 
 
 def cpu_threads():
@@ -331,7 +340,8 @@ def main():
         achieved = fl_pair / (pair_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "pair_mlp stage (%d launches/step)" % pair_launches,
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                "frac": achieved / pk["bf16_sustained"], "traffic": ncu_traffic("pair_mlp_kernel"),
+                "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic.json)",
                 "peak_source": pk["source"] + ", sustained dense bf16",
                 "algorithmic_flops_per_px": fl_head - fl_q, "ms_per_step": pair_ms,
                 "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
@@ -347,7 +357,7 @@ def main():
                        "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB",
                        "head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
                        "head_ms": ms_head, "eager_step_ms": ms_eager, "encoder_ms_est": ms_enc,
-                       "encoder": ("native RDN on tcgen05 (bf16x3 implicit GEMM, fp32-grade; csrc/rdn_tc.cu)"
+                       "encoder": ("native RDN on tcgen05 (fp16 hi/lo split implicit GEMM, fp32-grade; csrc/rdn_tc.cu)"
                                    if getattr(gen, "native_encoder", False) else
                                    "PyTorch RDN fp32 (cudnn.allow_tf32=%s, channels_last=%s)"
                                    % (torch.backends.cudnn.allow_tf32, bool(args.channels_last))),

@@ -73,6 +73,7 @@ def ncu_top(tag, rep="prof_head.ncu-rep"):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
+    traffic = {}
     with open(os.path.join(OUT, f"{tag}_ncu_top.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the tcgen05 kernels\n\n"
                 f"source report: gpurun_out/{rep} (scratch, not tracked); selected raw metrics per launch.\n")
@@ -88,8 +89,16 @@ def ncu_top(tag, rep="prof_head.ncu-rep"):
                 ur, uw = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
                 sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
                 f.write(f"\nDRAM traffic (read + write) per launch: {(rd * sc[ur] + wr * sc[uw]) / 1e9:.3f} GB\n")
+                m = re.search(r"(\w+_kernel)", d.get("Kernel Name", ""))
+                if m:
+                    traffic[m.group(1)] = {"dram_bytes_per_launch": rd * sc[ur] + wr * sc[uw], "profile": tag,
+                                           "ms": d.get("gpu__time_duration.sum")}
             except (KeyError, ValueError):
                 pass
+    if traffic:       # bench.py reads this for roofline.traffic
+        import json
+        with open(os.path.join(OUT, "ncu_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     print("wrote", f"{tag}_ncu_top.md")
 
 
