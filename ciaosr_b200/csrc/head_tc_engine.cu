@@ -307,7 +307,7 @@ static int run_lr_precompute_tc(const PlanLayout& L, const float* plan, const He
 // =====================================================================================================
 // host orchestration
 // =====================================================================================================
-struct TcBufs { float *Pk, *Pv, *G, *x; };
+struct TcBufs { float *Pk, *Pv, *G; split_t *x_hi, *x_lo; };
 static int tc_ldg() { return HID + 4; }
 
 static TcBufs tc_carve_ws(Arena& a, const PlanLayout& L, int B, int H, int W, int Q) {
@@ -317,7 +317,8 @@ static TcBufs tc_carve_ws(Arena& a, const PlanLayout& L, int B, int H, int W, in
   s.Pk = a.take<float>(npix * HID);
   s.Pv = a.take<float>(npix * HID);
   s.G = a.take<float>(npix * 9 * tc_ldg());
-  s.x = a.take<float>((size_t)B * Q * t.Dvp);
+  s.x_hi = a.take<split_t>((size_t)B * Q * t.Dvp);      // attended values, fp16 hi / lo halves (same bytes as fp32)
+  s.x_lo = a.take<split_t>((size_t)B * Q * t.Dvp);
   return s;
 }
 
@@ -344,15 +345,15 @@ static int tc_grid(int n_tiles, int CL) {
   const int want = (n_tiles + CL - 1) / CL * CL;
   return want < sms ? want : sms;
 }
-template <class Kernel, class Params>
-static int launch_clustered(Kernel kernel, int grid, int CL, cudaStream_t st, const Params& P) {
+template <class Kernel, class... Args>
+static int launch_clustered(Kernel kernel, int grid, int CL, cudaStream_t st, const Args&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(HEAD_THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, P);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, args...);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (err != cudaSuccess) {
     set_error("launch of a clustered tcgen05 kernel failed: %s", cudaGetErrorString(err));
@@ -393,7 +394,7 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     P.Pk = b.Pk; P.Pv = b.Pv; P.G = b.G; P.ldg = tc_ldg();
     P.consts = reinterpret_cast<const float*>(blob + t.pair_consts);
     P.blob = blob + t.pair_blob; P.units_per_tile = t.pair_units; P.units5 = t.units5;
-    P.x = b.x; P.total_rows = total_q * 4; P.n_tiles = (int)((P.total_rows + ROWS - 1) / ROWS);
+    P.x_hi = b.x_hi; P.x_lo = b.x_lo; P.total_rows = total_q * 4; P.n_tiles = (int)((P.total_rows + ROWS - 1) / ROWS);
     P.softmax_scale = L.softmax_scale;
     const int grid = tc_grid(P.n_tiles, CL);
     P.iters = (P.n_tiles + grid - 1) / grid;
@@ -403,14 +404,18 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
   {
     StageScope sc(4, st);
     QueryParams Qp;
-    Qp.x = b.x; Qp.Dvp = t.Dvp;
+    Qp.Dvp = t.Dvp;
+    CUtensorMap map_hi, map_lo;
+    if ((rc = tma_make_map_2d(&map_hi, b.x_hi, total_q, t.Dvp)) || (rc = tma_make_map_2d(&map_lo, b.x_lo, total_q, t.Dvp)))
+      return rc;
     Qp.consts = reinterpret_cast<const float*>(blob + t.query_consts);
     Qp.blob = blob + t.query_blob; Qp.units_per_tile = t.query_units; Qp.slabs1 = t.slabs1;
     Qp.lr = a.lr; Qp.coord = a.coord; Qp.H = a.H; Qp.W = a.W; Qp.Q = a.Q;
     Qp.out = a.out; Qp.total_q = total_q; Qp.n_tiles = (int)((total_q + ROWS - 1) / ROWS);
     const int grid = tc_grid(Qp.n_tiles, CL);
     Qp.iters = (Qp.n_tiles + grid - 1) / grid;
-    int rc2 = CL == 2 ? launch_clustered(query_mlp_kernel<2>, grid, 2, st, Qp) : launch_clustered(query_mlp_kernel<1>, grid, 1, st, Qp);
+    int rc2 = CL == 2 ? launch_clustered(query_mlp_kernel<2>, grid, 2, st, Qp, map_hi, map_lo)
+                      : launch_clustered(query_mlp_kernel<1>, grid, 1, st, Qp, map_hi, map_lo);
     if (rc2) return rc2;
   }
   return CIAOSR_OK;

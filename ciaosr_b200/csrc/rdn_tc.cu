@@ -30,8 +30,8 @@
 // Dense blocks never concatenate: every RDB owns one 576-channel buffer and each layer writes its 64
 // channels into its slice; the LFF output goes straight into the next block's buffer and the global
 // fusion buffer.  The residual trunk is kept in fp32.
-#include <cuda.h>
 #include "gemm_tc.cuh"
+#include "tma.cuh"
 #include "kernels.cuh"
 
 namespace ciaosr {
@@ -61,13 +61,6 @@ struct ConvParams {
   float* out_nchw;                     // final feature [B,64,H,W] or nullptr
 };
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
 // D[tmem] (+)= A[tmem] * B[smem]^T, B descriptor high word given explicitly (8-row-group stride varies)
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t b_hi32,
                                         uint32_t idesc, uint32_t accumulate) {
@@ -412,31 +405,17 @@ static RdnPlanLayout rdn_layout(const ciaosr_rdn_desc* d) {
 
 __global__ void rdn_copy64_kernel(float* dst, const float* src) { dst[threadIdx.x] = src[threadIdx.x]; }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-// 4-D map over a bf16 NHWC tensor [B, H, W, channels]: box = 64 channels x box_x x box_y x 1 image,
+// 4-D map over a 16-bit NHWC tensor [B, H, W, channels]: box = 64 channels x box_x x box_y x 1 image,
 // 128B swizzle, out-of-bounds elements read as zero (the convolution's padding)
 static int make_map(CUtensorMap* m, void* base, int B, int H, int W, int channels, int box_x, int box_y) {
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = tma_get_encode();
   CIAOSR_REQUIRE(enc != nullptr, CIAOSR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t gdim[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t gstride[3] = {(cuuint64_t)channels * 2, (cuuint64_t)W * channels * 2,
                                  (cuuint64_t)H * W * channels * 2};
   const cuuint32_t box[4] = {64, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstride, box, estr,
+  const CUresult r = enc(m, TMA_SPLIT_DTYPE, 4, base, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CIAOSR_REQUIRE(r == CUDA_SUCCESS, CIAOSR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);

@@ -9,6 +9,7 @@
 #pragma once
 #include "gemm_tc.cuh"
 #include "pairs.cuh"
+#include "tma.cuh"
 
 namespace ciaosr {
 
@@ -26,7 +27,7 @@ struct PairParams {
   const float* Pk; const float* Pv; const float* G; int ldg;
   const float* consts;        // 16 x 256 floats + bv5p[Dvp], see layout below
   const uint8_t* blob; int units_per_tile; int units5;
-  float* x;                   // [total_q, Dvp]
+  split_t* x_hi; split_t* x_lo;   // [total_q, Dvp] attended values, already split for the query kernel's UMMAs
   long long total_rows; int n_tiles; int iters;     // iters = tiles per CTA (uniform over the grid)
   float softmax_scale;
 };
@@ -276,10 +277,12 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
             const float send = (lane & 2) ? r16[i] : r16[8 + i];
             r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
           }
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(P.x + q * P.Dvp + cp0 + sub);
-            dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
-            dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
+          if (valid) {                                         // 8 columns = one 16-byte store per half
+            uint4 h, l;
+            split2(r8[0], r8[1], h.x, l.x); split2(r8[2], r8[3], h.y, l.y);
+            split2(r8[4], r8[5], h.z, l.z); split2(r8[6], r8[7], h.w, l.w);
+            *reinterpret_cast<uint4*>(P.x_hi + q * P.Dvp + cp0 + sub) = h;
+            *reinterpret_cast<uint4*>(P.x_lo + q * P.Dvp + cp0 + sub) = l;
           }
         }
         epi_release_d(s, e);
@@ -297,15 +300,22 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
 // query kernel: imnet_q + residual
 // =====================================================================================================
 struct QueryParams {
-  const float* x; int Dvp;                 // [total_q, Dvp]
+  int Dvp;                                 // x = x_hi + x_lo [total_q, Dvp] comes through the two tensor maps
   const float* consts;                     // x256 floats: 0..3 b_q(layers 1..4), 4..6 W5 rows, 7: b5 in [0..3)
   const uint8_t* blob; int units_per_tile; int slabs1;
   const float* lr; const float* coord; int H, W, Q;
   float* out; long long total_q; int n_tiles; int iters;
 };
 
+// Layer 1's A operand is x, which pair_mlp_kernel left in HBM already split into fp16 hi / lo: the producer
+// warp lands each [128 queries x 64 columns] slab pair straight in the operand slots with two 2-D TMA tile
+// loads (128B swizzle = the UMMA layout; rows past total_q read as zero), so the row threads touch layer 1
+// only to drain its accumulator.  A_READY counts NEPI/32 arrivals for the row-warp-written layers; for a TMA
+// slab the producer supplies all of them itself (one with the transaction byte count).
 template <int CL>
-__global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryParams P) {
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi,
+                 const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcShared s = tc_carve(smem);
   for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
@@ -316,11 +326,37 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
 
   if (warp == 0) {
     ProdState ps{0};
+    uint32_t afree_bits = 0xFu;            // parity to wait on next, per operand slot (same bookkeeping as the row threads)
+    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); }
     for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      const int row0 = (int)min(tile * ROWS, (long long)0x7FFFFF00);     // past the end: all rows read as zero
       const uint8_t* b = P.blob;
-      produce_job<CL>(s, ps, b, P.slabs1, 2, cta_rank);
+      // layer 1: A slabs (TMA) interleaved with their weight slabs, so neither ring starves the other
+      int a_next = 0;
+      for (int sl = 0; sl < P.slabs1; ++sl) {
+        // A slabs run up to 3 ahead of the weights (4 operand slots): block only for the slab needed now
+        while (a_next < P.slabs1 && a_next <= sl + 3) {
+          const int slot = a_next & 3;
+          const uint32_t fr = bar_at(s, BAR_A_FREE + slot), par = (afree_bits >> slot) & 1;
+          if (a_next == sl) mbar_wait(fr, par, 120 + slot);
+          else if (!__shfl_sync(0xffffffffu, (int)mbar_try_wait(fr, par), 0)) break;
+          afree_bits ^= 1u << slot;
+          if (lane == 0) {
+            const uint32_t rdy = bar_at(s, BAR_A_READY + slot);
+            mbar_arrive_expect_tx(rdy, 2 * SLAB_BYTES);
+            tma_load_2d(s.a_hi + slot * SLAB_BYTES, &map_hi, a_next * KSLAB, row0, rdy);
+            tma_load_2d(s.a_lo + slot * SLAB_BYTES, &map_lo, a_next * KSLAB, row0, rdy);
+            for (int k = 1; k < NEPI / 32; ++k) mbar_arrive(rdy);
+          }
+          __syncwarp();
+          ++a_next;
+        }
+        produce_job<CL>(s, ps, b + (size_t)sl * 2 * UNIT_BYTES, 1, 2, cta_rank);
+      }
       b += (size_t)P.slabs1 * 2 * UNIT_BYTES;
       for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
@@ -338,25 +374,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) query_mlp_kernel(const QueryP
       const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
       const long long g = tile * ROWS + row;
       const bool valid = tile < P.n_tiles && g < P.total_q;
-      const float4* xrow = valid ? reinterpret_cast<const float4*>(P.x + g * P.Dvp) + half * 8 : nullptr;
-      // layer-1 operand: x (fp32) -> bf16 hi/lo slabs, streamed through the 4 slots
-      float4 xb[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xb[j] = xrow ? __ldg(xrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-      for (int sl = 0; sl < P.slabs1; ++sl) {
-        const int slot = sl & 3;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { v[4 * j] = xb[j].x; v[4 * j + 1] = xb[j].y; v[4 * j + 2] = xb[j].z; v[4 * j + 3] = xb[j].w; }
-        if (sl + 1 < P.slabs1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xb[j] = xrow ? __ldg(xrow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        slab_begin(s, e, slot, true);
-        a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
-        if (sl & 1) slabs_done2(s, slot - 1, slot);            // slabs1 is even (Dvp % 128 == 0)
-      }
+      // layer-1 operand slabs are written by the producer warp (TMA); keep the slot parity bookkeeping in step
+      for (int sl = 0; sl < P.slabs1; ++sl) e.afree_bits ^= 1u << (sl & 3);
       epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst);
       epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + HID);
       epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + 2 * HID);

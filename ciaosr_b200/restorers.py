@@ -20,6 +20,24 @@ from .coords import make_coord
 from .metrics import psnr, ssim, tensor2img
 
 
+def _to_host(tensors):
+    """``{k: v.cpu()}`` (ciaosr.py:181-183) with ONE synchronisation: every CUDA tensor is copied into a fresh
+    page-locked host tensor (PyTorch's caching host allocator recycles the blocks) with non-blocking copies on
+    the current stream.  A pageable ``.cpu()`` stages through a bounce buffer at ~1/4 of the PCIe rate and
+    synchronises per tensor."""
+    out, dev = {}, None
+    for k, v in tensors.items():
+        if v.is_cuda:
+            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            h.copy_(v, non_blocking=True)
+            out[k], dev = h, v.device
+        else:
+            out[k] = v
+    if dev is not None:
+        torch.cuda.current_stream(dev).synchronize()
+    return out
+
+
 class BasicRestorer(nn.Module):
     allowed_metrics = {"PSNR": psnr, "SSIM": ssim}
 
@@ -85,9 +103,10 @@ class CiaoSR(BasicRestorer):
             assert gt is not None, "evaluation with metrics must have gt images."
             results = dict(eval_result=self.evaluate(pred, gt))
         else:
-            results = dict(lq=lq.cpu(), output=pred.cpu())
+            results = dict(lq=lq, output=pred)
             if gt is not None:
-                results["gt"] = gt.cpu()
+                results["gt"] = gt
+            results = _to_host(results)
         if save_image:
             import cv2
             key = "gt_path" if "gt_path" in meta[0] else "lq_path"
