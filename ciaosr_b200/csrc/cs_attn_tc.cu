@@ -71,8 +71,12 @@ __global__ void csa_knorm_batch_kernel(const float* __restrict__ r, float* __res
   }
 }
 
-// one warp per row; the row (L <= a few thousand) is cached in registers when it fits
-__global__ void softmax_rows_ld_kernel(float* __restrict__ s, long long rows, int L, int ld) {
+// One warp per row: softmax of the scores, written as the two 16-bit halves of P * 2^11 (row-major [rows, ldp],
+// columns L..ldp zero) that the P.V GEMM loads with TMA.  The power-of-two scale keeps small probabilities out
+// of fp16's subnormal range (absolute resolution 3e-11 instead of 6e-8); the P.V epilogue multiplies by 2^-11.
+constexpr float CSA_P_SCALE = 2048.0f;
+__global__ void softmax_rows_split_kernel(float* __restrict__ s, split_t* __restrict__ p_hi, split_t* __restrict__ p_lo,
+                                          long long rows, int L, int ld, int ldp) {
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -87,7 +91,16 @@ __global__ void softmax_rows_ld_kernel(float* __restrict__ s, long long rows, in
     sum += e;
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  for (int i = lane; i < L; i += 32) p[i] = __fdiv_rn(p[i], sum);
+  uint32_t* hi = reinterpret_cast<uint32_t*>(p_hi + row * ldp);
+  uint32_t* lo = reinterpret_cast<uint32_t*>(p_lo + row * ldp);
+  for (int i = 2 * lane; i < ldp; i += 64) {             // ldp % 8 == 0, L % 2 may be 1
+    const float a = i < L ? __fdiv_rn(p[i], sum) * CSA_P_SCALE : 0.0f;
+    const float b = i + 1 < L ? __fdiv_rn(p[i + 1], sum) * CSA_P_SCALE : 0.0f;
+    uint32_t h, l;
+    split2(a, b, h, l);
+    hi[i >> 1] = h;
+    lo[i >> 1] = l;
+  }
 }
 
 __global__ void csa_fold_batch_kernel(const float* __restrict__ o, float* __restrict__ cv, int Hp, int Wp,
@@ -190,34 +203,15 @@ struct ScoreEpi {           // S[m, n] = scale * acc, n < L
     }
   }
 };
-struct ProbGen {            // A = P rows (fp32, ld % 4 == 0), K = L
-  const float* p; int K, ld;
-  struct Row { const float* r; };
-  __device__ __forceinline__ Row row(long long m) const { return Row{p + m * ld}; }
-  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int k = k0 + 4 * g;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k + 4 <= K) q = __ldg(reinterpret_cast<const float4*>(r.r + k));
-      else if (k < K) {
-        q.x = r.r[k];
-        if (k + 1 < K) q.y = r.r[k + 1];
-        if (k + 2 < K) q.z = r.r[k + 2];
-      }
-      v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
-    }
-  }
-};
-struct OutEpi {             // O[m, n] = acc, n < N (N % 4 == 0); accumulate: O += acc (K chunks, see gemm_tc.cuh)
-  float* o; int N;
-  __device__ __forceinline__ void store(const ProbGen::Row&, long long m, int n0, const float (&v)[32]) const {
+struct OutEpi {             // O[m, n] = sc * acc, n < N (N % 4 == 0); accumulate: O += sc * acc (K chunks, see gemm_tc.cuh)
+  float* o; int N; float sc;
+  __device__ __forceinline__ void store(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
     float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (n0 + 4 * j < N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (n0 + 4 * j < N) dst[j] = make_float4(sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
   }
-  __device__ __forceinline__ void accumulate(const ProbGen::Row&, long long m, int n0, const float (&v)[32]) const {
+  __device__ __forceinline__ void accumulate(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
     float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
     float4 old[8];
 #pragma unroll
@@ -226,7 +220,8 @@ struct OutEpi {             // O[m, n] = acc, n < N (N % 4 == 0); accumulate: O 
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (n0 + 4 * j < N)
-        dst[j] = make_float4(old[j].x + v[4 * j], old[j].y + v[4 * j + 1], old[j].z + v[4 * j + 2], old[j].w + v[4 * j + 3]);
+        dst[j] = make_float4(fmaf(sc, v[4 * j], old[j].x), fmaf(sc, v[4 * j + 1], old[j].y),
+                             fmaf(sc, v[4 * j + 2], old[j].z), fmaf(sc, v[4 * j + 3], old[j].w));
   }
 };
 struct DownGen {            // rows = cropped output pixels (img, y, x); k = (u*3+v)*C + ci
@@ -281,14 +276,14 @@ struct DownEpi {            // (acc + b) / 6 -> NHWC slice and / or NCHW
 // ---- host orchestration ------------------------------------------------------------------------------
 struct CsaTcSizes {
   int Hp, Wp, Hl, Wl, L, ldS, HWp, group;      // group = images processed together
-  int Chp;
+  int Chp, ldP;                                // ldP: row stride of the split P matrices (16-bit elements, 16-byte rows)
   int kq_slabs, kq_units, vt_slabs, vt_units, dn_slabs, dn_units;
 };
 static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   CsaTcSizes s;
   s.Hp = H + (H & 1); s.Wp = W + (W & 1);
   s.Hl = s.Hp / 2; s.Wl = s.Wp / 2; s.L = s.Hl * s.Wl; s.ldS = (s.L + 3) / 4 * 4;
-  s.HWp = s.Hp * s.Wp;
+  s.HWp = s.Hp * s.Wp; s.ldP = (s.L + 7) / 8 * 8;
   s.Chp = (C / 2 + 3) / 4 * 4;                 // query-embedding channels, zero padded to the float4 gathers
   s.kq_slabs = (9 * s.Chp + KSLAB - 1) / KSLAB; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
   s.vt_slabs = (s.L + KSLAB - 1) / KSLAB; s.vt_units = (36 * C + UNIT_N - 1) / UNIT_N;
@@ -316,7 +311,7 @@ static int csa_kchunk() {
 
 bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
-struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; uint8_t *kblob, *vblob, *dblob; };
+struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; split_t *Ph, *Pl; uint8_t *kblob, *vblob, *dblob; };
 static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s, int B) {
   CsaTcBufs b;
   const int C = L.C, Ch = C / 2, g = s.group;
@@ -325,6 +320,8 @@ static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s
   b.R = a.take<float>((size_t)B * s.L * Ch);
   b.nrm = a.take<float>((size_t)B * s.L);
   b.S = a.take<float>((size_t)g * s.HWp * s.ldS);
+  b.Ph = a.take<split_t>((size_t)g * s.HWp * s.ldP);
+  b.Pl = a.take<split_t>((size_t)g * s.HWp * s.ldP);
   b.O = a.take<float>((size_t)g * s.HWp * 36 * C);
   b.cv = a.take<float>((size_t)g * 4 * s.HWp * C);
   b.kblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.kq_slabs, s.kq_units));
@@ -373,11 +370,13 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob,
                       QPatchGen{b.Mi, s.Hp, s.Wp, s.Chp, 9 * s.Chp, (long long)i0 * s.HWp},
                       ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st))) return rc;
-    CIAOSR_LAUNCH(softmax_rows_ld_kernel, cdiv(rows, 8), 256, 0, st, b.S, rows, s.L, s.ldS);
+    CIAOSR_LAUNCH(softmax_rows_split_kernel, cdiv(rows, 8), 256, 0, st, b.S, b.Ph, b.Pl, rows, s.L, s.ldS, s.ldP);
+    CUtensorMap map_hi, map_lo;
+    if ((rc = tma_make_map_2d(&map_hi, b.Ph, rows, s.ldP)) || (rc = tma_make_map_2d(&map_lo, b.Pl, rows, s.ldP))) return rc;
     if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
       return rc;
     if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, csa_kchunk()}, b.vblob,
-                      ProbGen{b.S, s.L, s.ldS}, OutEpi{b.O, 36 * C}, st))) return rc;
+                      TmaRowsGen{}, OutEpi{b.O, 36 * C, 1.0f / CSA_P_SCALE}, st, &map_hi, &map_lo))) return rc;
     const long long ctot = (long long)g * 4 * s.HWp * C;
     CIAOSR_LAUNCH(csa_fold_batch_kernel, cdiv(ctot, 256), 256, 0, st, b.O, b.cv, s.Hp, s.Wp, C, ctot);
     if ((rc = tc_gemm(GemmShape{(long long)g * H * W, s.dn_slabs, s.dn_units, (long long)g * H * W, 0}, b.dblob,

@@ -51,6 +51,20 @@ struct agen_combines : std::false_type {};
 template <class AGen>
 struct agen_combines<AGen, std::enable_if_t<AGen::kCombine>> : std::true_type {};
 
+// AGen::kTma = true: A is not generated but loaded -- it already sits in HBM as two row-major 16-bit matrices
+// (hi / lo halves, [M, K]) described by the two tensor maps passed to the launch; the producer warp lands the slabs
+// (produce_job_tma_a) and the row threads only drain accumulators.  fill() is never called.
+template <class AGen, class = void>
+struct agen_tma : std::false_type {};
+template <class AGen>
+struct agen_tma<AGen, std::enable_if_t<AGen::kTma>> : std::true_type {};
+struct TmaRowsGen {          // the generic "A comes through the tensor maps" generator
+  static constexpr bool kTma = true;
+  struct Row {};
+  __device__ __forceinline__ Row row(long long) const { return Row{}; }
+  __device__ __forceinline__ void fill(Row&, long long, int, float (&)[32]) const {}
+};
+
 template <class Epi, class Row, class = void>
 struct epi_accumulates : std::false_type {};
 template <class Epi, class Row>
@@ -60,7 +74,8 @@ struct epi_accumulates<Epi, Row, std::void_t<decltype(std::declval<const Epi&>()
 
 template <class AGen, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi) {
+tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi,
+               const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcShared s = tc_carve(smem);
   const uint32_t tmem_base = tc_prologue<1, TC_NEPI>(s, smem);
@@ -74,15 +89,21 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
 
   if (warp == 0) {
     ProdState ps{0};
+    uint32_t afree_bits = 0xFu;
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
       const int units = min(2, g.nunits - 2 * nc);
       const long long image = ((long long)mt * ROWS) / g.rows_per_image;
       // blob order: for chunk: for slab: for unit
       const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES;
-      for (int kc = 0; kc < n_kc; ++kc)
-        produce_job<1>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, min(kchunk, g.kslabs - kc * kchunk),
-                       units, 0);
+      for (int kc = 0; kc < n_kc; ++kc) {
+        const int ns = min(kchunk, g.kslabs - kc * kchunk);
+        if constexpr (agen_tma<AGen>::value)
+          produce_job_tma_a<1, TC_NEPI>(s, ps, afree_bits, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0,
+                                        &map_hi, &map_lo, kc * kchunk, mt * ROWS);
+        else
+          produce_job<1>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0);
+      }
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
@@ -107,6 +128,7 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
 #pragma unroll 1
         for (int sl = kc * kchunk; sl < sl_end; ++sl) {
           const int slot = sl & 3;
+          if constexpr (agen_tma<AGen>::value) { e.afree_bits ^= 1u << slot; continue; }   // producer-loaded slab
           float v[32];
           if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
           else {
@@ -151,8 +173,11 @@ inline int tc_grid_size(long long n_jobs) {
 }
 
 template <class AGen, class Epi>
-static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, const Epi& epi, cudaStream_t st) {
+static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, const Epi& epi, cudaStream_t st,
+                   const CUtensorMap* map_hi = nullptr, const CUtensorMap* map_lo = nullptr) {
   if (g.M <= 0) return CIAOSR_OK;
+  CIAOSR_REQUIRE(!agen_tma<AGen>::value || (map_hi && map_lo), CIAOSR_E_INVALID, "tc_gemm: tensor maps missing");
+  static const CUtensorMap no_map = {};
   static bool attr_set = false;      // one per template instantiation
   if (!attr_set) {
     CIAOSR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<AGen, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -165,7 +190,8 @@ static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, co
     CIAOSR_REQUIRE(can && g.kchunk % 4 == 0, CIAOSR_E_INVALID,
                    "tc_gemm: K chunking needs an accumulating epilogue and kchunk %% 4 == 0 (operand slots)");
   }
-  CIAOSR_LAUNCH((tc_gemm_kernel<AGen, Epi>), tc_grid_size(n_jobs), TC_THREADS, SM_TOTAL, st, g, blob, agen, epi);
+  CIAOSR_LAUNCH((tc_gemm_kernel<AGen, Epi>), tc_grid_size(n_jobs), TC_THREADS, SM_TOTAL, st, g, blob, agen, epi,
+                map_hi ? *map_hi : no_map, map_lo ? *map_lo : no_map);
   return CIAOSR_OK;
 }
 

@@ -333,27 +333,7 @@ query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi
       const int row0 = (int)min(tile * ROWS, (long long)0x7FFFFF00);     // past the end: all rows read as zero
       const uint8_t* b = P.blob;
       // layer 1: A slabs (TMA) interleaved with their weight slabs, so neither ring starves the other
-      int a_next = 0;
-      for (int sl = 0; sl < P.slabs1; ++sl) {
-        // A slabs run up to 3 ahead of the weights (4 operand slots): block only for the slab needed now
-        while (a_next < P.slabs1 && a_next <= sl + 3) {
-          const int slot = a_next & 3;
-          const uint32_t fr = bar_at(s, BAR_A_FREE + slot), par = (afree_bits >> slot) & 1;
-          if (a_next == sl) mbar_wait(fr, par, 120 + slot);
-          else if (!__shfl_sync(0xffffffffu, (int)mbar_try_wait(fr, par), 0)) break;
-          afree_bits ^= 1u << slot;
-          if (lane == 0) {
-            const uint32_t rdy = bar_at(s, BAR_A_READY + slot);
-            mbar_arrive_expect_tx(rdy, 2 * SLAB_BYTES);
-            tma_load_2d(s.a_hi + slot * SLAB_BYTES, &map_hi, a_next * KSLAB, row0, rdy);
-            tma_load_2d(s.a_lo + slot * SLAB_BYTES, &map_lo, a_next * KSLAB, row0, rdy);
-            for (int k = 1; k < NEPI / 32; ++k) mbar_arrive(rdy);
-          }
-          __syncwarp();
-          ++a_next;
-        }
-        produce_job<CL>(s, ps, b + (size_t)sl * 2 * UNIT_BYTES, 1, 2, cta_rank);
-      }
+      produce_job_tma_a<CL, NEPI>(s, ps, afree_bits, b, P.slabs1, 2, cta_rank, &map_hi, &map_lo, 0, row0);
       b += (size_t)P.slabs1 * 2 * UNIT_BYTES;
       for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
       afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads

@@ -28,6 +28,7 @@
 //   D_FREE[2]   NEPI/32 row warps   row threads -> UMMA issuer          (accumulator drained)
 #pragma once
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace ciaosr {
 using namespace tc;
@@ -122,6 +123,40 @@ __device__ __forceinline__ void produce_job(const TcShared& s, ProdState& ps, co
       __syncwarp();
     }
     ps.phase ^= 1;
+  }
+}
+
+// One job whose A operand already sits in HBM as two row-major 16-bit matrices (hi, lo halves): the producer
+// lands each [128 rows x 64 K] slab pair in the operand slots with two 2-D TMA tile loads (128B swizzle = the
+// UMMA layout; rows / columns outside the matrix read as zero) and interleaves them with the job's weight
+// slabs.  A slabs run up to 3 ahead of the weights (4 operand slots): the warp blocks only for the slab it
+// needs now.  A_READY counts NEPI/32 arrivals (row-warp-written slabs); for a TMA slab the producer supplies
+// all of them itself, one carrying the transaction byte count.  `afree_bits`: parity to wait on next per slot.
+template <int CL, int NEPI>
+__device__ __forceinline__ void produce_job_tma_a(const TcShared& s, ProdState& ps, uint32_t& afree_bits,
+                                                  const uint8_t* blob, int nslabs, int units, uint32_t cta_rank,
+                                                  const CUtensorMap* map_hi, const CUtensorMap* map_lo, int kslab0,
+                                                  int row0) {
+  const int lane = threadIdx.x & 31;
+  int a_next = 0;
+  for (int sl = 0; sl < nslabs; ++sl) {
+    while (a_next < nslabs && a_next <= sl + 3) {
+      const int slot = a_next & 3;
+      const uint32_t fr = bar_at(s, BAR_A_FREE + slot), par = (afree_bits >> slot) & 1;
+      if (a_next == sl) mbar_wait(fr, par, 120 + slot);
+      else if (!__shfl_sync(0xffffffffu, (int)mbar_try_wait(fr, par), 0)) break;
+      afree_bits ^= 1u << slot;
+      if (lane == 0) {
+        const uint32_t rdy = bar_at(s, BAR_A_READY + slot);
+        mbar_arrive_expect_tx(rdy, 2 * SLAB_BYTES);
+        tma_load_2d(s.a_hi + slot * SLAB_BYTES, map_hi, (kslab0 + a_next) * KSLAB, row0, rdy);
+        tma_load_2d(s.a_lo + slot * SLAB_BYTES, map_lo, (kslab0 + a_next) * KSLAB, row0, rdy);
+        for (int k = 1; k < NEPI / 32; ++k) mbar_arrive(rdy);
+      }
+      __syncwarp();
+      ++a_next;
+    }
+    produce_job<CL>(s, ps, blob + (size_t)sl * units * UNIT_BYTES, 1, units, cta_rank);
   }
 }
 
