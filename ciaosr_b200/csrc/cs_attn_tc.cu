@@ -71,36 +71,70 @@ __global__ void csa_knorm_batch_kernel(const float* __restrict__ r, float* __res
   }
 }
 
-// One warp per row: softmax of the scores, written as the two 16-bit halves of P * 2^11 (row-major [rows, ldp],
-// columns L..ldp zero) that the P.V GEMM loads with TMA.  The power-of-two scale keeps small probabilities out
+// Softmax of the scores, written as the two 16-bit halves of P * 2^11 (row-major [rows, ldp], columns L..ldp
+// zero) that the P.V GEMM loads with TMA.  The power-of-two scale keeps small probabilities out
 // of fp16's subnormal range (absolute resolution 3e-11 instead of 6e-8); the P.V epilogue multiplies by 2^-11.
 constexpr float CSA_P_SCALE = 2048.0f;
-__global__ void softmax_rows_split_kernel(float* __restrict__ s, split_t* __restrict__ p_hi, split_t* __restrict__ p_lo,
-                                          long long rows, int L, int ld, int ldp) {
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  float* p = s + row * ld;
+// One 256-thread block per row, the row cached in registers (NE values per thread): S is read once.
+template <int NE>
+__global__ void __launch_bounds__(256) softmax_rows_split_kernel(const float* __restrict__ s, split_t* __restrict__ p_hi,
+                                                                 split_t* __restrict__ p_lo, int L, int ld, int ldp) {
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float2* p = reinterpret_cast<const float2*>(s + row * ld);      // ld % 4 == 0
+  __shared__ float red[8];
+  float2 v[NE / 2];
   float mx = -INFINITY;
-  for (int i = lane; i < L; i += 32) mx = fmaxf(mx, p[i]);
+#pragma unroll
+  for (int j = 0; j < NE / 2; ++j) {
+    const int i = 2 * (t + 256 * j);
+    v[j] = make_float2(-INFINITY, -INFINITY);
+    if (i + 1 < L) v[j] = p[t + 256 * j];
+    else if (i < L) v[j].x = s[row * ld + i];
+    mx = fmaxf(mx, fmaxf(v[j].x, v[j].y));
+  }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
   float sum = 0.0f;
-  for (int i = lane; i < L; i += 32) {
-    const float e = expf(p[i] - mx);
-    p[i] = e;
-    sum += e;
+#pragma unroll
+  for (int j = 0; j < NE / 2; ++j) {
+    v[j].x = expf(v[j].x - mx);          // exp(-inf) = 0 for the padding
+    v[j].y = expf(v[j].y - mx);
+    sum += v[j].x + v[j].y;
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) sum += red[w];
   uint32_t* hi = reinterpret_cast<uint32_t*>(p_hi + row * ldp);
   uint32_t* lo = reinterpret_cast<uint32_t*>(p_lo + row * ldp);
-  for (int i = 2 * lane; i < ldp; i += 64) {             // ldp % 8 == 0, L % 2 may be 1
-    const float a = i < L ? __fdiv_rn(p[i], sum) * CSA_P_SCALE : 0.0f;
-    const float b = i + 1 < L ? __fdiv_rn(p[i + 1], sum) * CSA_P_SCALE : 0.0f;
-    uint32_t h, l;
-    split2(a, b, h, l);
-    hi[i >> 1] = h;
-    lo[i >> 1] = l;
+#pragma unroll
+  for (int j = 0; j < NE / 2; ++j) {
+    const int i = 2 * (t + 256 * j);
+    if (i < ldp) {                                            // ldp % 8 == 0; columns L..ldp are written as zero
+      uint32_t h, l;
+      split2(__fdiv_rn(v[j].x, sum) * CSA_P_SCALE, __fdiv_rn(v[j].y, sum) * CSA_P_SCALE, h, l);
+      hi[i >> 1] = h;
+      lo[i >> 1] = l;
+    }
   }
+}
+static int softmax_rows_split(const float* s, split_t* p_hi, split_t* p_lo, long long rows, int L, int ld, int ldp,
+                              cudaStream_t st) {
+  CIAOSR_REQUIRE(L <= 256 * 128, CIAOSR_E_INVALID,
+                 "cross-scale attention (tcgen05): %d keys per image exceed the softmax kernel's 32768; tile the input "
+                 "(test_cfg.tile) or use the fp32 engine", L);
+  if (L <= 256 * 8) CIAOSR_LAUNCH(softmax_rows_split_kernel<8>, (unsigned)rows, 256, 0, st, s, p_hi, p_lo, L, ld, ldp);
+  else if (L <= 256 * 40) CIAOSR_LAUNCH(softmax_rows_split_kernel<40>, (unsigned)rows, 256, 0, st, s, p_hi, p_lo, L, ld, ldp);
+  else CIAOSR_LAUNCH(softmax_rows_split_kernel<128>, (unsigned)rows, 256, 0, st, s, p_hi, p_lo, L, ld, ldp);
+  return CIAOSR_OK;
 }
 
 __global__ void csa_fold_batch_kernel(const float* __restrict__ o, float* __restrict__ cv, int Hp, int Wp,
@@ -370,7 +404,7 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob,
                       QPatchGen{b.Mi, s.Hp, s.Wp, s.Chp, 9 * s.Chp, (long long)i0 * s.HWp},
                       ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st))) return rc;
-    CIAOSR_LAUNCH(softmax_rows_split_kernel, cdiv(rows, 8), 256, 0, st, b.S, b.Ph, b.Pl, rows, s.L, s.ldS, s.ldP);
+    if ((rc = softmax_rows_split(b.S, b.Ph, b.Pl, rows, s.L, s.ldS, s.ldP, st))) return rc;
     CUtensorMap map_hi, map_lo;
     if ((rc = tma_make_map_2d(&map_hi, b.Ph, rows, s.ldP)) || (rc = tma_make_map_2d(&map_lo, b.Pl, rows, s.ldP))) return rc;
     if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
