@@ -188,42 +188,35 @@ struct DownSrc {            // B[n = co, k = (u*3+v)*C + ci] = down_wt[k, co]
 };
 
 // ---- A generators / epilogues ----------------------------------------------------------------------
-struct QPatchGen {          // rows = (img, y, x) of the group; k = t*Ch + c; Ch = padded row stride of Mi, % 4 == 0
-  const float* mi; int Hp, Wp, Ch, K; long long pix0;
-  struct Row { int y, x; long long pix; };
-  __device__ __forceinline__ Row row(long long m) const {
-    const long long p = pix0 + m;
-    const int r = (int)(p % ((long long)Hp * Wp));
-    return Row{r / Wp, r % Wp, p};
+// Q operand of the score GEMM: 3x3 zero-padded patches of Mi (k = t*Chp + c), materialised ONCE per pass as the
+// two 16-bit halves [rows, ldq] that the GEMM then loads with TMA for each of its L/256 column chunks (generating
+// the patches in the GEMM's row threads re-gathered and re-split them per chunk: 36x on a 192x192 tile).
+__global__ void csa_qpatch_split_kernel(const float* __restrict__ mi, split_t* __restrict__ q_hi,
+                                        split_t* __restrict__ q_lo, int Hp, int Wp, int Chp, int ldq, long long pix0,
+                                        long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;      // one thread per 4 columns
+  if (i >= total) return;
+  const int per_row = ldq / 4;
+  const long long m = i / per_row;
+  const int k = (int)(i % per_row) * 4;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < 9 * Chp) {
+    const long long pix = pix0 + m;
+    const int r = (int)(pix % ((long long)Hp * Wp)), y = r / Wp, x = r % Wp;
+    const int t = k / Chp, c = k - t * Chp;
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    if (y + dy >= 0 && y + dy < Hp && x + dx >= 0 && x + dx < Wp)
+      q = __ldg(reinterpret_cast<const float4*>(mi + (pix + dy * Wp + dx) * Chp + c));
   }
-  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
-    const float* self = mi + r.pix * Ch;       // loads are unconditional (masked afterwards): all 8 in flight together
-    const float* src[8];
-    bool ok[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int k = k0 + 4 * g;
-      src[g] = self; ok[g] = false;
-      if (k < K) {
-        const int t = k / Ch, c = k - t * Ch;
-        const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
-        ok[g] = r.y + dy >= 0 && r.y + dy < Hp && r.x + dx >= 0 && r.x + dx < Wp;
-        if (ok[g]) src[g] = self + (dy * Wp + dx) * Ch + c;
-      }
-    }
-    float4 q[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
-      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
-    }
-  }
-};
+  uint2 h, l;
+  split2(q.x, q.y, h.x, l.x);
+  split2(q.z, q.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(q_hi + m * ldq + k) = h;
+  *reinterpret_cast<uint2*>(q_lo + m * ldq + k) = l;
+}
 struct ScoreEpi {           // S[m, n] = scale * acc, n < L
   float* s; int L, ld; float scale;
-  __device__ __forceinline__ void store(const QPatchGen::Row&, long long m, int n0, const float (&v)[32]) const {
+  __device__ __forceinline__ void store(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
     float* dst = s + m * ld + n0;
     if (n0 + 32 <= L) {
 #pragma unroll
@@ -310,7 +303,7 @@ struct DownEpi {            // (acc + b) / 6 -> NHWC slice and / or NCHW
 // ---- host orchestration ------------------------------------------------------------------------------
 struct CsaTcSizes {
   int Hp, Wp, Hl, Wl, L, ldS, HWp, group;      // group = images processed together
-  int Chp, ldP;                                // ldP: row stride of the split P matrices (16-bit elements, 16-byte rows)
+  int Chp, ldP, ldQ;                                // ldP: row stride of the split P matrices (16-bit elements, 16-byte rows)
   int kq_slabs, kq_units, vt_slabs, vt_units, dn_slabs, dn_units;
 };
 static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
@@ -319,7 +312,7 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   s.Hl = s.Hp / 2; s.Wl = s.Wp / 2; s.L = s.Hl * s.Wl; s.ldS = (s.L + 3) / 4 * 4;
   s.HWp = s.Hp * s.Wp; s.ldP = (s.L + 7) / 8 * 8;
   s.Chp = (C / 2 + 3) / 4 * 4;                 // query-embedding channels, zero padded to the float4 gathers
-  s.kq_slabs = (9 * s.Chp + KSLAB - 1) / KSLAB; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
+  s.kq_slabs = (9 * s.Chp + KSLAB - 1) / KSLAB; s.ldQ = (9 * s.Chp + 7) / 8 * 8; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
   s.vt_slabs = (s.L + KSLAB - 1) / KSLAB; s.vt_units = (36 * C + UNIT_N - 1) / UNIT_N;
   s.dn_slabs = (9 * C + KSLAB - 1) / KSLAB; s.dn_units = (C + UNIT_N - 1) / UNIT_N;
   // images per pass: tiles must not straddle images, and the score tensor stays <= 1 GiB
@@ -345,7 +338,7 @@ static int csa_kchunk() {
 
 bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
-struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; split_t *Ph, *Pl; uint8_t *kblob, *vblob, *dblob; };
+struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; split_t *Ph, *Pl, *Qh, *Ql; uint8_t *kblob, *vblob, *dblob; };
 static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s, int B) {
   CsaTcBufs b;
   const int C = L.C, Ch = C / 2, g = s.group;
@@ -354,6 +347,8 @@ static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s
   b.R = a.take<float>((size_t)B * s.L * Ch);
   b.nrm = a.take<float>((size_t)B * s.L);
   b.S = a.take<float>((size_t)g * s.HWp * s.ldS);
+  b.Qh = a.take<split_t>((size_t)g * s.HWp * s.ldQ);
+  b.Ql = a.take<split_t>((size_t)g * s.HWp * s.ldQ);
   b.Ph = a.take<split_t>((size_t)g * s.HWp * s.ldP);
   b.Pl = a.take<split_t>((size_t)g * s.HWp * s.ldP);
   b.O = a.take<float>((size_t)g * s.HWp * 36 * C);
@@ -401,9 +396,16 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     const long long rows = (long long)g * s.HWp;
     if ((rc = tc_pack_operand(b.kblob, g, s.L, 9 * s.Chp, kstride, KhatSrc{b.R, b.nrm, s.Hl, s.Wl, Ch, s.Chp, i0}, st)))
       return rc;
-    if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob,
-                      QPatchGen{b.Mi, s.Hp, s.Wp, s.Chp, 9 * s.Chp, (long long)i0 * s.HWp},
-                      ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st))) return rc;
+    {
+      const long long total = rows * (s.ldQ / 4);
+      CIAOSR_LAUNCH(csa_qpatch_split_kernel, cdiv(total, 256), 256, 0, st, b.Mi, b.Qh, b.Ql, s.Hp, s.Wp, s.Chp, s.ldQ,
+                    (long long)i0 * s.HWp, total);
+      CUtensorMap qmap_hi, qmap_lo;
+      if ((rc = tma_make_map_2d(&qmap_hi, b.Qh, rows, s.ldQ)) || (rc = tma_make_map_2d(&qmap_lo, b.Ql, rows, s.ldQ)))
+        return rc;
+      if ((rc = tc_gemm(GemmShape{rows, s.kq_slabs, s.kq_units, s.HWp, kstride}, b.kblob, TmaRowsGen{},
+                        ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st, &qmap_hi, &qmap_lo))) return rc;
+    }
     if ((rc = softmax_rows_split(b.S, b.Ph, b.Pl, rows, s.L, s.ldS, s.ldP, st))) return rc;
     CUtensorMap map_hi, map_lo;
     if ((rc = tma_make_map_2d(&map_hi, b.Ph, rows, s.ldP)) || (rc = tma_make_map_2d(&map_lo, b.Pl, rows, s.ldP))) return rc;
