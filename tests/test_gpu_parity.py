@@ -307,3 +307,31 @@ def test_untiled_large_scale_properties():
     assert max_abs(sub, full[:, idx]) < TOL
     nl_simt = plan.cross_scale_attention(feat, engine="simt")
     assert max_abs(nl, nl_simt) < TOL
+
+
+def test_evaluate_on_device_matches_host_metrics():
+    """forward_test with metrics (basic_restorer.py:101-124): CUDA frames are scored on the device; the numbers
+    must equal the host (numpy) metrics on the same frames, which are pinned to the reference's functions."""
+    from ciaosr_b200 import metrics
+    from ciaosr_b200.builder import build
+    from ciaosr_b200.restorers import CiaoSR
+    from tests.util import generator_cfg
+    dev = _dev()
+    s = 3
+    m = build(dict(type=CiaoSR, generator=generator_cfg(16, [32, 32], 500), pixel_loss=dict(type="L1Loss"),
+                   rgb_mean=(0.4488, 0.4371, 0.4040), rgb_std=(1., 1., 1.)),
+              test_cfg=dict(scale=s, metrics=["PSNR", "SSIM"], crop_border=s, convert_to="y"))
+    synth.fill_module(m.generator, 3)
+    m = m.eval().to(dev)
+    h, w = 20, 24
+    lq = (synth.synth_lr_image(1, h, w, 3) + torch.tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1)).clamp(0, 1).to(dev)
+    coord = make_coord((h * s, w * s)).unsqueeze(0).to(dev)
+    cell = make_cell((h * s, w * s), coord.shape[1]).unsqueeze(0).to(dev)
+    gt = torch.nn.functional.interpolate(lq, scale_factor=s, mode="bicubic").clamp(0, 1)
+    gt_q = gt.permute(0, 2, 3, 1).reshape(1, -1, 3).contiguous()                  # [B, Q, 3] as the pipeline gives it
+    res = m(lq=lq, gt=gt_q, test_mode=True, coord=coord, cell=cell)["eval_result"]
+    m.test_cfg = dict(scale=s)
+    out = m(lq=lq, gt=None, test_mode=True, coord=coord, cell=cell)["output"]
+    a, b = metrics.tensor2img(out), metrics.tensor2img(gt.cpu())
+    assert abs(res["PSNR"] - metrics.psnr(a, b, s, convert_to="y")) < 1e-4
+    assert abs(res["SSIM"] - metrics.ssim(a, b, s, convert_to="y")) < 1e-6
