@@ -162,6 +162,8 @@ class HeadPlan:
             if tuple(nonlocal_feat.shape) != (B, self.n_nonlocal, H, W):
                 raise ValueError("nonlocal_feat has the wrong shape")
         out = torch.empty(B, q, 3, dtype=torch.float32, device=feature.device)
+        if q == 0:                       # an empty coordinate list gives an empty prediction, as in the reference
+            return out
         nbytes = self.workspace_bytes(B, H, W, q, engine)
         ws = self._workspace(nbytes)
         with torch.cuda.device(self.device):

@@ -335,3 +335,27 @@ def test_evaluate_on_device_matches_host_metrics():
     a, b = metrics.tensor2img(out), metrics.tensor2img(gt.cpu())
     assert abs(res["PSNR"] - metrics.psnr(a, b, s, convert_to="y")) < 1e-4
     assert abs(res["SSIM"] - metrics.ssim(a, b, s, convert_to="y")) < 1e-6
+
+
+def test_edge_shapes_vs_oracle():
+    """Empty, single-query and minimum-size inputs (the smallest map cross-scale attention's reflect padding
+    admits is 2x2), odd sizes and a ragged last 128-row tile, on every engine that supports the head."""
+    from oracle import ciaosr_oracle as orc
+    dev = _dev()
+    meta = dict(c=64, hidden=[256, 256, 256, 256], eval_bsize=None, local_size=2, non_local=True, seed=51)
+    for engine in _engines(meta):
+        g = build_generator(meta, dev, engine=engine)
+        w = head_weights(g)
+        for b, h, wd, nq in [(1, 2, 2, None), (1, 3, 5, 1), (2, 5, 3, 33), (1, 4, 4, 0)]:
+            feat = synth.synth_feature(b, 64, h, wd, 51)
+            lq = synth.synth_lr_image(b, h, wd, 51)
+            coord = make_coord((h * 3, wd * 3)).unsqueeze(0).expand(b, -1, 2).contiguous()
+            if nq is not None:
+                coord = coord[:, :nq].contiguous()
+            cell = make_cell((h * 3, wd * 3), max(coord.shape[1], 1)).unsqueeze(0).expand(b, -1, 2)[:, :coord.shape[1]].contiguous()
+            g.gen_feature = lambda _x, _f=feat.to(dev): [_f]
+            out = g(lq.to(dev), coord.to(dev), cell.to(dev), test_mode=True).cpu()
+            assert out.shape == (b, coord.shape[1], 3)
+            if coord.shape[1]:
+                ref = orc.head_forward(lq, feat, coord, cell, w, eval_bsize=None)
+                assert max_abs(out, ref) < TOL, (engine, b, h, wd, nq)
