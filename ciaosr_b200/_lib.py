@@ -12,8 +12,9 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_lon
 ABI_VERSION = 1
 MAX_LAYERS = 8
 MAX_SCALES = 4
-N_STAGES = 6
-STAGE_NAMES = ("layout", "cross_scale_attn", "lr_precompute", "pair_mlp", "query_mlp", "rdn_encoder")
+N_STAGES = 7
+STAGE_NAMES = ("layout", "cross_scale_attn", "lr_precompute", "pair_mlp", "query_mlp", "rdn_encoder",
+               "encoder_linear")
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
@@ -31,6 +32,7 @@ EXPORTS = (
     "ciaosr_cross_scale_attn_workspace_bytes", "ciaosr_cross_scale_attn_forward", "ciaosr_query_rgb_forward",
     "ciaosr_tile_blend_accumulate", "ciaosr_tile_blend_finish",
     "ciaosr_rdn_plan_bytes", "ciaosr_rdn_plan_init", "ciaosr_rdn_workspace_bytes", "ciaosr_rdn_forward",
+    "ciaosr_linear_plan_bytes", "ciaosr_linear_plan_init", "ciaosr_linear_forward",
 )
 
 
@@ -64,6 +66,11 @@ class RdnDesc(Structure):
                 ("dense_w", POINTER(c_void_p)), ("dense_b", POINTER(c_void_p)),
                 ("lff_w", POINTER(c_void_p)), ("lff_b", POINTER(c_void_p)),
                 ("gff0_w", c_void_p), ("gff0_b", c_void_p), ("gff1_w", c_void_p), ("gff1_b", c_void_p)]
+
+
+class LinearDesc(Structure):
+    _fields_ = [("abi_version", c_int32), ("in_features", c_int32), ("out_features", c_int32),
+                ("weight", c_void_p), ("bias", c_void_p)]
 
 
 class CiaoSRNativeError(RuntimeError):
@@ -123,6 +130,10 @@ def load():
     lib.ciaosr_rdn_workspace_bytes.argtypes = [POINTER(RdnDesc), c_int, c_int, c_int, POINTER(c_size_t)]
     lib.ciaosr_rdn_forward.argtypes = [POINTER(RdnDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_size_t, c_void_p]
+    lib.ciaosr_linear_plan_bytes.argtypes = [POINTER(LinearDesc), POINTER(c_size_t)]
+    lib.ciaosr_linear_plan_init.argtypes = [POINTER(LinearDesc), c_void_p, c_size_t, c_void_p]
+    lib.ciaosr_linear_forward.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_longlong, c_int, c_void_p,
+                                          c_void_p]
     for name in EXPORTS[3:]:  # everything after the three non-int getters
         getattr(lib, name).restype = c_int
     if lib.ciaosr_abi_version() != ABI_VERSION:

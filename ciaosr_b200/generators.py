@@ -243,6 +243,9 @@ class LocalImplicitSRSWINIR(LocalImplicitSRNet):
         self.patch_unembed = self.encoder.patch_unembed
         self.conv_after_body = self.encoder.conv_after_body
         del self.encoder
+        # encoder fast path: the trunk's Linear layers through the library's fp32-grade
+        # tensor-core Linear (swinir.native_linear).  'auto' = on for CUDA inference; False keeps plain PyTorch.
+        self.native_encoder = "auto"
 
     def forward_features(self, x):
         x_size = (x.shape[2], x.shape[3])
@@ -255,7 +258,9 @@ class LocalImplicitSRSWINIR(LocalImplicitSRNet):
         _, _, h, w = img.size()
         pad_h = (self.window_size - h % self.window_size) % self.window_size
         pad_w = (self.window_size - w % self.window_size) % self.window_size
+        from . import swinir
         x = self.conv_first(F.pad(img, (0, pad_w, 0, pad_h), "reflect"))
-        res = self.conv_after_body(self.forward_features(x))
+        with swinir.native_linear(bool(self.native_encoder) and img.is_cuda and not torch.is_grad_enabled()):
+            res = self.conv_after_body(self.forward_features(x))
         res += x
         return [res[:, :, :h, :w]]

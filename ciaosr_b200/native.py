@@ -297,3 +297,42 @@ class RdnPlan:
                                                       _ptr(out), _ptr(self._ws), self._ws.numel(),
                                                       _stream(self.device)))
         return out
+
+
+class LinearPlan:
+    """One nn.Linear packed for ``ciaosr_linear_forward`` (fp32-grade Linear on the tensor cores; the SwinIR
+    trunk's qkv / proj / fc1 / fc2).  Holds references to the fp32 weight / bias it was packed from."""
+
+    def __init__(self, weight, bias):
+        lib = _lib.load()
+        self.weight = _f32c(weight.detach(), "weight")
+        self.bias = _f32c(bias.detach(), "bias") if bias is not None else None
+        self.device = self.weight.device
+        d = _lib.LinearDesc()
+        d.abi_version = _lib.ABI_VERSION
+        d.out_features, d.in_features = self.weight.shape
+        d.weight = self.weight.data_ptr()
+        d.bias = self.bias.data_ptr() if self.bias is not None else None
+        self.desc = d
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.ciaosr_linear_plan_bytes(ctypes.byref(d), ctypes.byref(n)))
+        with torch.cuda.device(self.device):
+            self.buf = torch.empty(max(n.value, 256), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.ciaosr_linear_plan_init(ctypes.byref(d), _ptr(self.buf), n.value, _stream(self.device)))
+
+    @staticmethod
+    def supports(weight):
+        return weight.is_cuda and weight.dtype == torch.float32 and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0
+
+    def forward(self, x, gelu=False):
+        """x [..., in_features] fp32 CUDA -> [..., out_features]."""
+        x = _f32c(x, "x")
+        k, n = self.desc.in_features, self.desc.out_features
+        if x.shape[-1] != k:
+            raise ValueError(f"linear expects {k} input features, got {x.shape[-1]}")
+        rows = x.numel() // k
+        out = torch.empty(*x.shape[:-1], n, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ciaosr_linear_forward(ctypes.byref(self.desc), _ptr(self.buf), _ptr(x), rows,
+                                                         1 if gelu else 0, _ptr(out), _stream(self.device)))
+        return out

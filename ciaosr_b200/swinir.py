@@ -27,6 +27,46 @@ def _pair(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
+# ---- encoder fast path: the trunk's Linear layers on the tensor cores -------------------------
+# The trunk's FLOPs are its Linear layers (qkv, proj, fc1, fc2; K = 180 / 360).  Parity with the fp32 reference
+# rules out TF32 (features ~1e-3 off), and cuBLAS' fp32 CUDA-core sgemm runs these shapes at ~14 TFLOP/s (12 of the
+# 29 ms a 128x128 tile spends in the trunk).  Inside `native_linear(True)` they go through the library's
+# `ciaosr_linear_forward` instead: the fp16 hi/lo-split tcgen05 GEMM of the head (fp32-grade) with bias and the
+# exact GELU fused in its epilogue.  Everything else of the trunk stays plain PyTorch.
+_NATIVE = False
+
+
+class native_linear:
+    """Context manager: route this module's nn.Linear layers through the native tensor-core Linear."""
+
+    def __init__(self, enabled):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        global _NATIVE
+        self.prev, _NATIVE = _NATIVE, self.enabled
+
+    def __exit__(self, *exc):
+        global _NATIVE
+        _NATIVE = self.prev
+
+
+def _linear(x, lin, gelu=False):
+    """`lin(x)` (optionally followed by the exact GELU) for an nn.Linear."""
+    w = lin.weight
+    if _NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
+        from . import native
+        if native.LinearPlan.supports(w):
+            key = (w.data_ptr(), w._version, None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+            cache = lin.__dict__.get("_native_plan")
+            if cache is None or cache[0] != key:
+                cache = (key, native.LinearPlan(w, lin.bias))
+                lin.__dict__["_native_plan"] = cache
+            return cache[1].forward(x, gelu=gelu)
+    y = lin(x)
+    return F.gelu(y) if gelu else y
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (timm.models.layers.DropPath); identity in eval mode."""
 
@@ -53,7 +93,9 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        if isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none":
+            return self.drop(_linear(self.drop(_linear(x, self.fc1, gelu=True)), self.fc2))
+        return self.drop(_linear(self.drop(self.act(_linear(x, self.fc1))), self.fc2))
 
 
 def relative_position_index(window):
@@ -105,7 +147,7 @@ class WindowAttention(nn.Module):
     def forward(self, x, mask=None):
         """x [B * nW, N, C]; mask [nW, N, N] additive or None."""
         b_, n, c = x.shape
-        qkv = self.qkv(x).view(b_, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
+        qkv = _linear(x, self.qkv).view(b_, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
         add = self.bias().unsqueeze(0)                                  # [1, nH, N, N]
         if mask is not None:
             nw = mask.shape[0]
@@ -114,7 +156,7 @@ class WindowAttention(nn.Module):
         out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=add.to(x.dtype),
                                              dropout_p=self.attn_drop.p if self.training else 0.0,
                                              scale=self.scale)
-        return self.proj_drop(self.proj(out.transpose(1, 2).reshape(b_, n, c)))
+        return self.proj_drop(_linear(out.transpose(1, 2).reshape(b_, n, c), self.proj))
 
 
 class SwinTransformerBlock(nn.Module):

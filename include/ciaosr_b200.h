@@ -124,8 +124,8 @@ int ciaosr_engine_supported(const ciaosr_head_desc* desc, int engine);
  * elapsed milliseconds per stage into ms[0..n) / launches[0..n) and clears the
  * list.  Stages: 0 layout, 1 cross-scale attention, 2 LR precompute,
  * 3 (query,neighbour) MLP stacks + inner attention, 4 query MLP + residual,
- * 5 native RDN encoder. */
-#define CIAOSR_N_STAGES 6
+ * 5 native RDN encoder, 6 encoder Linear layers (ciaosr_linear_forward). */
+#define CIAOSR_N_STAGES 7
 int ciaosr_profile_enable(int on);
 int ciaosr_profile_read(float* ms, int* launches, int n);
 
@@ -196,6 +196,25 @@ int ciaosr_rdn_workspace_bytes(const ciaosr_rdn_desc* desc, int B, int H, int W,
 /* x [B,3,H,W] (normalised LR image, NCHW fp32) -> feature [B,64,H,W] NCHW fp32 */
 int ciaosr_rdn_forward(const ciaosr_rdn_desc* desc, const void* plan, const float* x, int B, int H,
                        int W, float* feature, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fp32-grade Linear on the tensor cores (SURVEY.md 8f "next" #2) ---------------
+ * out[rows, out_features] = act(x[rows, in_features] . weight^T + bias): the nn.Linear
+ * layers of the SwinIR trunk (qkv / proj / fc1 / fc2, swinir_net.py:15-31, 66-146) that
+ * LocalImplicitSRSWINIR.gen_feature runs (ciaosr_net.py:475-525).  weight [out, in]
+ * row-major fp32 as in the state_dict, bias [out] or NULL; in/out multiples of 4.
+ * activation: 0 none, 1 exact GELU (nn.GELU()).  Same fp16 hi/lo split arithmetic as the
+ * head (fp32-grade; TF32 would put the features ~1e-3 off). */
+typedef struct ciaosr_linear_desc {
+  int32_t abi_version;
+  int32_t in_features, out_features;
+  const float* weight;
+  const float* bias;
+} ciaosr_linear_desc;
+
+int ciaosr_linear_plan_bytes(const ciaosr_linear_desc* desc, size_t* bytes);
+int ciaosr_linear_plan_init(const ciaosr_linear_desc* desc, void* plan, size_t plan_bytes, void* stream);
+int ciaosr_linear_forward(const ciaosr_linear_desc* desc, const void* plan, const float* x, long long rows,
+                          int activation, float* out, void* stream);
 
 /* ---- tiled inference epilogue (ciaosr.py:218-258, 160-163) -------------- */
 /* acc/cnt [B,3,Ho,Wo] += tile prediction [B, th*tw, 3] placed at (y0,x0).   */

@@ -359,3 +359,57 @@ def test_edge_shapes_vs_oracle():
             if coord.shape[1]:
                 ref = orc.head_forward(lq, feat, coord, cell, w, eval_bsize=None)
                 assert max_abs(out, ref) < TOL, (engine, b, h, wd, nq)
+
+
+def test_native_linear_matches_fp64():
+    """ciaosr_linear_forward (fp32-grade Linear on tcgen05, optional exact GELU) vs a float64 PyTorch Linear:
+    SwinIR's shapes (K = 180 / 360, N = 540 / 180 / 360), ragged row counts, with and without bias."""
+    from ciaosr_b200 import native
+    dev = _dev()
+    g = torch.Generator().manual_seed(7)
+    for rows, k, n, gelu, bias in [(1000, 180, 540, False, True), (64 * 9 + 5, 180, 180, False, True),
+                                   (4096, 180, 360, True, True), (300, 360, 180, False, False), (1, 4, 4, True, True)]:
+        x = torch.randn(rows, k, generator=g)
+        w = torch.randn(n, k, generator=g) / k ** 0.5
+        b = torch.randn(n, generator=g) * 0.1 if bias else None
+        ref = x.double() @ w.double().t() + (b.double() if bias else 0.0)
+        if gelu:
+            ref = torch.nn.functional.gelu(ref)
+        plan = native.LinearPlan(w.to(dev), b.to(dev) if bias else None)
+        out = plan.forward(x.to(dev).view(1, rows, k), gelu=gelu).cpu()
+        assert out.shape == (1, rows, n)
+        err = float((out[0].double() - ref).abs().max())
+        fp32 = float(((x @ w.t() + (b if bias else 0.0)).double() - (x.double() @ w.double().t() + (b.double() if bias else 0.0))).abs().max())
+        assert err < 2e-5 and err < 20 * max(fp32, 1e-7), (rows, k, n, err, fp32)     # within ~3x of fp32's own rounding
+
+
+def test_swinir_native_linear_trunk():
+    """SwinIR trunk with its Linear layers on the native tensor-core path vs the plain fp32 PyTorch trunk, and the
+    effect on the head's output (C = 180) at the O(1) feature spread the tolerance is stated for."""
+    from ciaosr_b200.builder import build
+    from ciaosr_b200.generators import LocalImplicitSRSWINIR
+    from ciaosr_b200.swinir import SwinIR
+    dev = _dev()
+    mlp = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3, hidden_list=[256, 256, 256, 256])
+    enc = dict(type=SwinIR, upscale=4, in_chans=3, img_size=48, window_size=8, img_range=1., depths=[2, 2],
+               embed_dim=180, num_heads=[6, 6], mlp_ratio=2, upsampler="pixelshuffle", resi_connection="1conv")
+    g = build(dict(type=LocalImplicitSRSWINIR, window_size=8, encoder=enc, imnet_q=mlp(), imnet_k=mlp(),
+                   imnet_v=mlp(), feat_unfold=True, eval_bsize=30000))
+    synth.fill_module(g, 17)
+    g = g.eval().to(dev)
+    for b, h, w in [(1, 24, 40), (2, 19, 21)]:                  # window multiple; reflect-padded
+        x = synth.synth_lr_image(b, h, w, 17).to(dev)
+        with torch.no_grad():
+            g.native_encoder = False
+            ref = g.gen_feature(x)[0]
+            g.native_encoder = "auto"
+            out = g.gen_feature(x)[0]
+        assert out.shape == ref.shape == (b, 180, h, w)
+        scale = float(ref.abs().max())
+        assert 0.0 < max_abs(out, ref) < 2e-5 * max(1.0, scale), (max_abs(out, ref), scale)
+        k = 0.5 / float(ref.std())
+        coord = make_coord((h * 2, w * 2)).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        cell = make_cell((h * 2, w * 2), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        y0 = g.query_rgb([(ref * k).contiguous()], coord, cell)
+        y1 = g.query_rgb([(out * k).contiguous()], coord, cell)
+        assert max_abs(y0, y1) < TOL
