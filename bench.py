@@ -239,6 +239,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = bool(args.encoder_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     model = build_model(args.engine).to(dev)
+    model.test_cfg["shard_queries"] = False        # weak scaling: every rank runs its own batch end to end
     gen = model.generator
     if args.channels_last:
         gen.to(memory_format=torch.channels_last)

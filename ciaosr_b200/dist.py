@@ -64,6 +64,28 @@ def sharded_batch_forward(generator, lq, coord, cell, group=None):
     return torch.cat(all_gather_padded(local, counts, group), dim=0)
 
 
+def sharded_query_forward(generator, lq, coord, cell, eval_bsize=None, group=None):
+    """Split the QUERY axis of one un-tiled call across ranks (BASELINE config 3, x6 / x8 on a whole frame):
+    every rank runs the encoder and the cross-scale attention on the full LR input (they are replicated: a few
+    per cent of the work at these scales), evaluates a contiguous band of the coordinate list, and one all-gather
+    assembles [B, Q, 3].  Band boundaries are multiples of `eval_bsize`, because the reference reads tx, ty from
+    the first cell of every eval_bsize-chunk (ciaosr_net.py:162-163 via :243): aligned bands see the same chunk
+    starts as the unsharded call, so the result is identical."""
+    rank, ws = world()
+    q = coord.shape[1]
+    unit = int(eval_bsize) if eval_bsize else 1
+    n_units = -(-q // unit)
+    bounds = [min(shard_range(n_units, r, ws)[0] * unit, q) for r in range(ws)] + [q]
+    s, e = bounds[rank], bounds[rank + 1]
+    if e > s:
+        local = generator(lq, coord[:, s:e].contiguous(), cell[:, s:e].contiguous(), test_mode=True)
+    else:
+        local = lq.new_zeros((lq.shape[0], 0, 3))
+    counts = [bounds[r + 1] - bounds[r] for r in range(ws)]
+    parts = all_gather_padded(local.transpose(0, 1).contiguous(), counts, group)       # gather along the query axis
+    return torch.cat(parts, dim=0).transpose(0, 1).contiguous()
+
+
 def sharded_tile_predictions(origins, run_tile, tile_shape, like, group=None):
     """Deal `origins` (list of (y0, x0)) round-robin to the ranks, evaluate the local ones with
     `run_tile(y0, x0) -> [B, th*tw, 3]`, all-gather.  Returns predictions for ALL tiles in

@@ -91,7 +91,11 @@ class CiaoSR(BasicRestorer):
             if self.test_cfg is not None and self.test_cfg.get("tile", None):
                 pred = self.clip_test(lq, model, denorm=True)
             else:
-                pred = model(lq, coord, cell, test_mode=True)
+                if cdist.world()[1] > 1 and lq.shape[0] == 1 and (self.test_cfg or {}).get("shard_queries", True):
+                    # one process per GPU: bands of the coordinate list per rank, one all-gather (dist.py)
+                    pred = cdist.sharded_query_forward(model, lq, coord, cell, getattr(model, "eval_bsize", None))
+                else:
+                    pred = model(lq, coord, cell, test_mode=True)
                 pred = pred * self.gt_std + self.gt_mean
                 pred.clamp_(0, 1)
         ih, iw = lq.shape[-2:]

@@ -44,6 +44,18 @@ def _worker(rank, ws, port, tmp):
         full = _fake_generator(lq, coord, cell)
         out = cd.sharded_batch_forward(_fake_generator, lq, coord, cell)
         assert out.shape == full.shape and torch.equal(out, full)
+        # query-axis bands aligned to eval_bsize (chunk-start cells must be the same as unsharded)
+        def chunky(lq_, coord_, cell_, test_mode=True, bs=4):
+            outs = []
+            for l in range(0, coord_.shape[1], bs):                  # like batched_predict: first cell of each chunk
+                seed = cell_[:, l:l + 1, :1]
+                outs.append(_fake_generator(lq_, coord_[:, l:l + bs], cell_[:, l:l + bs]) + seed)
+            return torch.cat(outs, 1) if outs else lq_.new_zeros((lq_.shape[0], 0, 3))
+        for bs in (4, 3, None):
+            gen = (lambda a, b, c, test_mode=True, bs=bs: chunky(a, b, c, bs=bs)) if bs else _fake_generator
+            ref = gen(lq, coord, cell)
+            got = cd.sharded_query_forward(gen, lq, coord, cell, eval_bsize=bs)
+            assert got.shape == ref.shape and torch.equal(got, ref), bs
         # uneven padded gather
         counts = [3, 1]
         t = torch.full((counts[rank], 2), float(rank))

@@ -157,7 +157,12 @@ def main():
             with torch.no_grad():
                 if model.test_cfg.get("tile"):
                     return model.clip_test(x, g, denorm=True)
-                return (g(x, kw["coord"], kw["cell"], test_mode=True) * model.gt_std + model.gt_mean).clamp_(0, 1)
+                if world > 1:       # bands of the coordinate list per rank, one all-gather (ciaosr_b200/dist.py)
+                    from ciaosr_b200 import dist as cdist
+                    p = cdist.sharded_query_forward(g, x, kw["coord"], kw["cell"], g.eval_bsize)
+                else:
+                    p = g(x, kw["coord"], kw["cell"], test_mode=True)
+                return (p * model.gt_std + model.gt_mean).clamp_(0, 1)
 
         torch.cuda.reset_peak_memory_stats(dev)
         out = run()
@@ -186,6 +191,17 @@ def main():
                     tiles=(len(m.tile_origins(h, min(test_cfg["tile"], h, w), test_cfg["tile_overlap"])) *
                            len(m.tile_origins(w, min(test_cfg["tile"], h, w), test_cfg["tile_overlap"]))
                            if test_cfg.get("tile") else 1))
+        if world > 1 and args.check:
+            # the sharded frame must equal the frame this rank computes alone (no collective inside)
+            x = (lq - m.lq_mean.to(lq)) / m.lq_std.to(lq)
+            with torch.no_grad():
+                if test_cfg.get("tile"):
+                    m.test_cfg["shard_tiles"] = False
+                    alone = m.clip_test(x, gen, denorm=True)
+                    m.test_cfg["shard_tiles"] = True
+                else:
+                    alone = (gen(x, kw["coord"], kw["cell"], test_mode=True) * m.gt_std + m.gt_mean).clamp_(0, 1)
+            line["check_sharded_vs_single_max_abs"] = float((alone - out).abs().max())
         if args.stages and world == 1:
             # one eager pass with the library's per-stage CUDA events; "encoder+glue" is the remainder
             from ciaosr_b200 import native
