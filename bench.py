@@ -201,10 +201,24 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; see main() for why fd 1 is redirected."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    # Libraries print to fd 1 behind Python's back (NCCL writes "NCCL version ..." there when NCCL_DEBUG is set):
+    # keep a private copy of stdout for the JSON line and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -375,7 +389,7 @@ def main():
             log(f"cpu baseline done: {ms:.0f} ms per sample on {threads} threads")
             line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
                                     "sample": "1 of the 16 crops (36 864 px), 2 timed runs, %.0f ms each" % ms}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
