@@ -101,7 +101,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -111,10 +111,22 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in [t0, t1] (the timed region).  nvidia-smi
+        needs a few hundred ms to start on an 8-GPU box, so the sampler is started before the warm-up and the
+        window is cut out afterwards; if the region was shorter than the sampling period, the samples closest
+        to it (within 1 s) are used."""
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = list(self.lines)
+        if t0 is not None:
+            inside = [ln for ts, ln in lines if t0 <= ts <= t1]
+            if not inside:
+                near = sorted(lines, key=lambda p: min(abs(p[0] - t0), abs(p[0] - t1)))[:2]
+                inside = [ln for ts, ln in near if min(abs(ts - t0), abs(ts - t1)) < 1.0]
+        else:
+            inside = [ln for _, ln in lines]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -314,13 +326,26 @@ def main():
         return float(t.item()) / steps, launches, stages
 
     log("model + inputs ready")
-    for _ in range(args.warmup):
-        step_device()
-    torch.cuda.synchronize()
-    log("warm-up done")
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            step_device()
+        torch.cuda.synchronize()
+        log("warm-up done")
+        t_start = time.time()
         ms_step, launches, _ = timed(step_device, args.steps)
-    clocks = clk.summary()
+        t_end = time.time()
+        if not any(t_start <= ts <= t_end for ts, _ in clk.lines):
+            # the timed region was shorter than nvidia-smi's start-up: keep the GPU under the same load until a
+            # sample has been taken (untimed; the reported time is the one measured above)
+            deadline = time.time() + 3.0
+            n0 = len(clk.lines)
+            t_start = time.time()
+            while len(clk.lines) < n0 + 2 and time.time() < deadline:
+                with torch.no_grad():
+                    gen(lq_d, coord_d, cell_d, test_mode=True)      # no collective: ranks may loop differently
+                torch.cuda.synchronize()
+            t_end = time.time()
+    clocks = clk.summary(t_start, t_end)
     log(f"timed region done: {ms_step:.2f} ms/step")
     # stage timing needs the library's host code to run (it records CUDA events around its stages), so it
     # is taken in eager mode right after; the same kernels run when the step is replayed from a graph
