@@ -413,3 +413,40 @@ def test_swinir_native_linear_trunk():
         y0 = g.query_rgb([(ref * k).contiguous()], coord, cell)
         y1 = g.query_rgb([(out * k).contiguous()], coord, cell)
         assert max_abs(y0, y1) < TOL
+
+
+def test_engines_agree_on_random_shapes():
+    """Seeded sweep over channel counts (incl. C = 4, 12, 36: chunks straddle taps, Dv far from a multiple of 128),
+    odd / non-square maps, fractional scales, batch sizes, query subsets and both head variants: the tensor-core
+    engine (incl. tensor-core cross-scale attention) against the fp32 CUDA-core engine, which the golden tests pin
+    to the reference."""
+    import random
+    dev = _dev()
+    rnd = random.Random(1234)
+    for case in range(14):
+        c = rnd.choice([4, 12, 36, 64, 100, 180])
+        non_local = rnd.random() < 0.6
+        b, h, w = rnd.choice([1, 1, 2, 3]), rnd.randint(2, 21), rnd.randint(2, 21)
+        s = rnd.choice([1.3, 2, 2.5, 3, 4, 4.7])
+        meta = dict(c=c, hidden=[256, 256, 256, 256], eval_bsize=rnd.choice([None, 100, 30000]), local_size=2,
+                    non_local=non_local, seed=100 + case)
+        g = build_generator(meta, dev)
+        plan = g.head_plan()
+        assert plan.engine_supported("tcgen05"), meta
+        th, tw = max(1, round(h * s)), max(1, round(w * s))
+        feat = (synth.synth_feature(b, c, h, w, 100 + case) * (0.5 if c <= 64 else 0.35)).to(dev)
+        lq = synth.synth_lr_image(b, h, w, 100 + case).to(dev)
+        coord = make_coord((th, tw)).unsqueeze(0).expand(b, -1, 2).contiguous()
+        cell = make_cell((th, tw), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous()
+        if rnd.random() < 0.5:                               # a ragged subset in shuffled order
+            idx = torch.randperm(coord.shape[1], generator=torch.Generator().manual_seed(case))[:rnd.randint(1, coord.shape[1])]
+            coord, cell = coord[:, idx].contiguous(), cell[:, idx].contiguous()
+        coord, cell = coord.to(dev), cell.to(dev)
+        outs = {}
+        for engine in ("tcgen05", "simt"):
+            nl = plan.cross_scale_attention(feat, engine=engine) if non_local else None
+            outs[engine] = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl,
+                                          eval_bsize=meta["eval_bsize"], engine=engine)
+        assert torch.isfinite(outs["tcgen05"]).all(), (case, meta)
+        err = max_abs(outs["tcgen05"], outs["simt"])
+        assert err < TOL, (case, meta, b, h, w, s, err, float(outs["simt"].abs().max()))
