@@ -86,7 +86,7 @@ def sharded_query_forward(generator, lq, coord, cell, eval_bsize=None, group=Non
     return torch.cat(parts, dim=0).transpose(0, 1).contiguous()
 
 
-def sharded_tile_predictions(origins, run_tile, tile_shape, like, group=None):
+def sharded_tile_predictions(origins, run_tile, tile_shape, like, group=None, run_many=None):
     """Deal `origins` (list of (y0, x0)) round-robin to the ranks, evaluate the local ones with
     `run_tile(y0, x0) -> [B, th*tw, 3]`, all-gather.  Returns predictions for ALL tiles in
     `origins` order, so that every rank can blend the full frame locally (the blend is the
@@ -96,7 +96,9 @@ def sharded_tile_predictions(origins, run_tile, tile_shape, like, group=None):
     mine = shard_round_robin(n, rank, ws)
     counts = [len(shard_round_robin(n, r, ws)) for r in range(ws)]
     if mine:
-        local = torch.stack([run_tile(*origins[i]) for i in mine], dim=0)
+        # run_many evaluates a list of tiles (possibly several per generator call), run_tile one at a time
+        preds = run_many([origins[i] for i in mine]) if run_many is not None else [run_tile(*origins[i]) for i in mine]
+        local = torch.stack(preds, dim=0)
     else:
         local = like.new_zeros((0,) + tuple(tile_shape))
     gathered = all_gather_padded(local, counts, group)

@@ -162,14 +162,30 @@ class CiaoSR(BasicRestorer):
         cell[:, :, 0] *= 2 / th
         cell[:, :, 1] *= 2 / tw
 
-        def run_tile(y0, x0):
-            patch = img_lq[..., y0:y0 + tile, x0:x0 + tile].contiguous()
-            return model(patch, hr_coord, cell, test_mode=True)
+        # Tiles are independent generator calls (ciaosr.py:233-245) of one shape, so several of them ride in the
+        # batch dimension of ONE call: per-tile kernels of a 128x128 tile are too small to fill 148 SMs (the
+        # SwinIR trunk's Linear layers have 128 row tiles), and batch items are independent, so the result is
+        # the same.  test_cfg['tile_batch'] overrides the group size.
+        group = int(self.test_cfg.get("tile_batch", 0)) or max(1, min(8, round(73728 / (tile * tile))))
+
+        def run_tiles(batch):
+            """[(y0, x0), ...] -> list of [b, th*tw, 3] predictions, one generator call."""
+            t = len(batch)
+            patch = torch.cat([img_lq[..., y0:y0 + tile, x0:x0 + tile] for y0, x0 in batch], dim=0).contiguous()
+            out = model(patch, hr_coord.repeat(t, 1, 1) if t > 1 else hr_coord,
+                        cell.repeat(t, 1, 1) if t > 1 else cell, test_mode=True)
+            return list(out.split(b, dim=0))
+
+        def run_many(tiles):
+            preds = []
+            for i in range(0, len(tiles), group):
+                preds += run_tiles(tiles[i:i + group])
+            return preds
 
         if cdist.world()[1] > 1 and self.test_cfg.get("shard_tiles", True):
-            preds = cdist.sharded_tile_predictions(origins, run_tile, (b, th * tw, 3), img_lq)
+            preds = cdist.sharded_tile_predictions(origins, None, (b, th * tw, 3), img_lq, run_many=run_many)
         else:
-            preds = (run_tile(y0, x0) for y0, x0 in origins)
+            preds = run_many(origins)
         for (y0, x0), out in zip(origins, preds):
             native.tile_blend_accumulate(out, acc, cnt, y0 * sf, x0 * sf, th, tw)
         if denorm:
