@@ -450,3 +450,39 @@ def test_engines_agree_on_random_shapes():
         assert torch.isfinite(outs["tcgen05"]).all(), (case, meta)
         err = max_abs(outs["tcgen05"], outs["simt"])
         assert err < TOL, (case, meta, b, h, w, s, err, float(outs["simt"].abs().max()))
+
+
+@pytest.mark.parametrize("config", [3, 5])
+def test_full_size_models_engines_agree(config):
+    """BASELINE.json configs 3 and 5 with their full models and tile sizes (tools/run_configs.py runs whole frames):
+    config 3 = RDN 16x8 + cross-scale attention, 256x256 LR -> x4, tile 192 / overlap 32 (4 tiles, 1 Mpix out);
+    config 5 = real-world 002: SwinIR 6x6 (C = 180), no cross-scale attention / residual, EMA generator, x4,
+    tile 128 / overlap 32 on a 224x224 crop (4 tiles).  Product path (tcgen05 engine, native encoder paths, tiles
+    batched per call) vs the all-fp32 path (CUDA-core engine, PyTorch fp32 encoder): max-abs within the tolerance."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_configs as rc
+    from ciaosr_b200.builder import build
+    dev = _dev()
+    if config == 3:
+        cfg, test_cfg = rc.rdn_model(dict(scale=4, tile=192, tile_overlap=32))
+        n = 256
+    else:
+        cfg, test_cfg = rc.swinir_model(dict(scale=4, tile=128, tile_overlap=32), real=True)
+        n = 224
+    m = build(cfg, test_cfg=test_cfg)
+    synth.fill_module(m.generator, 0)
+    if getattr(m, "generator_ema", None) is not None:
+        m.generator_ema.load_state_dict(m.generator.state_dict())
+    m = m.eval().to(dev)
+    g = m._test_generator()
+    if config == 5:
+        rc.calibrate_features(g, dev)
+    lq = (synth.synth_lr_image(1, n, n, 7) + torch.tensor(rc.RGB_MEAN).view(1, 3, 1, 1)).to(dev)
+    a = m(lq=lq, gt=None, test_mode=True)["output"]
+    g.engine, g.native_encoder = "simt", False
+    b = m(lq=lq, gt=None, test_mode=True)["output"]
+    assert a.shape == (1, 3, 4 * n, 4 * n) and torch.isfinite(a).all()
+    assert 0.02 < float(a.std())
+    assert max_abs(a, b) < TOL
