@@ -73,9 +73,10 @@ def build_loss(cfg):
 
 
 def _populate():
-    from . import encoders, refiners, swinir
+    from . import encoders, pipelines, refiners, swinir
     _REGISTRY.update({"RDN": encoders.RDN, "EDSR": encoders.EDSR, "SwinIR": swinir.SwinIR,
-                      "MLPRefiner": refiners.MLPRefiner, "L1Loss": L1Loss})
+                      "MLPRefiner": refiners.MLPRefiner, "L1Loss": L1Loss,
+                      "GenerateCoordinateAndCell": pipelines.GenerateCoordinateAndCell})
 
 
 def load_checkpoint(module, filename, map_location="cpu", strict=False, revise_keys=((r"^module\.", ""),)):

@@ -1,5 +1,2 @@
-from ._placeholder import placeholder
-
-_W = "mmedited/datasets/pipelines/generate_assistant.py"
-GenerateCoordinateAndCell = placeholder("GenerateCoordinateAndCell", _W)
-GenerateCoordinateAndCell1 = placeholder("GenerateCoordinateAndCell1", _W)
+from ciaosr_b200.pipelines import (GenerateCoordinateAndCell, GenerateCoordinateAndCell1,  # noqa: F401
+                                   GenerateCoordinateAndCell2)
