@@ -410,10 +410,10 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()
-            val, ms = cpu_reference_sample(2, 1, threads)
+            val, ms = cpu_reference_sample(5, 1, threads)
             log(f"cpu baseline done: {ms:.0f} ms per sample on {threads} threads")
             line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
-                                    "sample": "1 of the 16 crops (36 864 px), 2 timed runs, %.0f ms each" % ms}
+                                    "sample": "1 of the 16 crops (36 864 px), 5 timed runs, %.0f ms each" % ms}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
