@@ -85,12 +85,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
 
   if (warp == 0) {
     ProdState ps{0};
-#ifdef CIAOSR_TC_QUARTER
-    uint32_t stage = 0;
-#define PAIR_PRODUCE(b, ns, un) produce_job_q<CL>(s, ps, stage, b, ns, un, cta_rank)
-#else
 #define PAIR_PRODUCE(b, ns, un) produce_job<CL>(s, ps, b, ns, un, cta_rank)
-#endif
     for (int it = 0; it < P.iters; ++it) {
       const uint8_t* b = P.blob;
       for (int j = 0; j < 6; ++j) { PAIR_PRODUCE(b, 4, 2); b += (size_t)8 * UNIT_BYTES; }
@@ -102,12 +97,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
-#ifdef CIAOSR_TC_QUARTER
-    uint32_t stage = 0;
-#define PAIR_MMA(ns, un, an) mma_job_q<CL>(s, tmem_base, m, stage, ns, un, an)
-#else
 #define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an)
-#endif
     for (int it = 0; it < P.iters; ++it) {
       for (int j = 0; j < 6; ++j) PAIR_MMA(4, 2, true);
       for (int c = 0; c < nchunks5; ++c) PAIR_MMA(4, min(2, P.units5 - 2 * c), c == 0);

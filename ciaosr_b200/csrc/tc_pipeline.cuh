@@ -242,87 +242,6 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
   ++m.jobctr;
 }
 
-#ifdef CIAOSR_TC_QUARTER
-// ---- alternative issue order: "quarter jobs" with N = 128 UMMAs ------------------------------------------
-// for each pair of K-slabs kg: for each 128-column half nh: slabs 2kg, 2kg+1 x unit nh.  The first column
-// half of a layer completes one quarter before the second, so the row threads convert it while the tensor
-// core still works on the second half.  Ring stages are used one by one (no pairing).
-template <int CL>
-__device__ __forceinline__ void produce_job_q(const TcShared& s, ProdState& ps, uint32_t& stage, const uint8_t* blob,
-                                              int nslabs, int units, uint32_t cta_rank) {
-  const bool leader = (threadIdx.x & 31) == 0;
-  const int ngroups = (nslabs + 1) >> 1;
-  for (int kg = 0; kg < ngroups; ++kg)
-    for (int u = 0; u < units; ++u)
-      for (int sl = 2 * kg; sl < min(2 * kg + 2, nslabs); ++sl)
-        for (int lo = 0; lo < 2; ++lo) {
-          mbar_wait(bar_at(s, BAR_W_EMPTY + stage), ps.phase ^ 1, 100 + stage);
-          if (leader) {
-            const uint32_t full = bar_at(s, BAR_W_FULL + stage);
-            mbar_arrive_expect_tx(full, SLAB_BYTES);
-            const uint8_t* src = blob + ((size_t)(sl * units + u) * 2 + lo) * SLAB_BYTES;
-            const uint32_t dst = s.w + stage * SLAB_BYTES;
-            if (CL == 1) bulk_g2s(dst, src, SLAB_BYTES, full);
-            else if ((uint32_t)lo == cta_rank) bulk_g2s_mc(dst, src, SLAB_BYTES, full, (uint16_t)((1u << CL) - 1));
-          }
-          __syncwarp();
-          if (++stage == W_STAGES) { stage = 0; ps.phase ^= 1; }
-        }
-}
-
-template <int CL>
-__device__ __forceinline__ void mma_job_q(const TcShared& s, uint32_t tmem_base, MmaState& m, uint32_t& stage,
-                                          int nslabs, int units, bool a_new) {
-  const bool leader = (threadIdx.x & 31) == 0;
-  const uint32_t idesc = make_idesc_split(ROWS, UNIT_N);
-  const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
-  mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
-  tc_fence_after();
-  const int ngroups = (nslabs + 1) >> 1;
-  for (int kg = 0; kg < ngroups; ++kg) {
-    for (int u = 0; u < units; ++u) {
-      const uint32_t dcol = tmem_base + d * 256 + u * UNIT_N;
-      for (int sl = 2 * kg; sl < min(2 * kg + 2, nslabs); ++sl) {
-        const int slot = sl & 3;
-        if (a_new && u == 0) {
-          mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
-          m.aready_bits ^= 1u << slot;
-        }
-        const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
-        mbar_wait(bar_at(s, BAR_W_FULL + stage), m.wphase, 220);
-        tc_fence_after();
-        if (leader) {
-          const uint32_t b = desc_lo(s.w + stage * SLAB_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_lo(dcol, a_lo + 2 * ks, b + 2 * ks, idesc, (sl | ks) != 0 ? 1u : 0u);
-            umma_lo(dcol, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
-          }
-          release_stage<CL>(s, stage);
-        }
-        __syncwarp();
-        if (++stage == W_STAGES) { stage = 0; m.wphase ^= 1; }
-        mbar_wait(bar_at(s, BAR_W_FULL + stage), m.wphase, 221);
-        tc_fence_after();
-        if (leader) {
-          const uint32_t b = desc_lo(s.w + stage * SLAB_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_lo(dcol, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
-          release_stage<CL>(s, stage);
-          if (u == units - 1) umma_commit(bar_at(s, BAR_A_FREE + slot));
-        }
-        __syncwarp();
-        if (++stage == W_STAGES) { stage = 0; m.wphase ^= 1; }
-      }
-      if (kg == ngroups - 1) {
-        if (leader) umma_commit(bar_at(s, BAR_D_READY + 2 * d + u));
-        __syncwarp();
-      }
-    }
-  }
-  ++m.jobctr;
-}
-#endif
 
 // ---- row-thread helpers --------------------------------------------------------------------------------
 // afree_bits / dready_bits: parity to wait on next, per operand slot / per (accumulator, column half)
