@@ -1,7 +1,7 @@
 // Cross-scale non-local attention on the tensor cores (arch_csnln.py:430-532).
 //
 // Same attention form as cs_attn.cu (see its header), with the three large contractions on
-// tcgen05 through the generic functor GEMM (gemm_tc.cuh, bf16x3 = fp32-grade):
+// tcgen05 through the generic functor GEMM (gemm_tc.cuh, fp16 hi/lo split x3 = fp32-grade):
 //   S = 10 * Q K^T        A = 3x3 patches of Mi (implicit), B = normalised 3x3 patches of R (packed per image)
 //   O = P V               A = softmax rows,                 B = V^T: 6x6 stride-2 patches of E (packed per image)
 //   out = down(canvas)/6  A = 3x3 stride-2 patches of the folded canvas, B = down-conv weights

@@ -1,14 +1,14 @@
 // Generic tcgen05 GEMM with functor-generated A rows:  C[m, n] = sum_k A(m, k) * B[n, k]
 //
 //   A  is produced on the fly, one thread per row (implicit im2col / patch extraction / pair
-//      products), split into bf16 hi/lo and written into the SW128 operand slabs;
+//      products), split into fp16 hi/lo and written into the SW128 operand slabs;
 //   B  is a pre-swizzled unit blob ([128 N x 64 K] hi+lo, 32 KB each) in global memory: static
 //      weights packed at plan time, or per-image operands packed by a small kernel just before;
 //   C  leaves through an epilogue functor that sees 32 consecutive columns of one row.
 //
 // A job = (128-row tile, N-chunk of <= 256 columns); A is regenerated per job (K may exceed the
 // 256 columns that fit the four operand slots, so slabs stream through them under A_FREE).
-// Same pipeline, barriers and bf16x3 arithmetic as head_tc.cu (tc_pipeline.cuh).
+// Same pipeline, barriers and split arithmetic as the head kernels (tc_pipeline.cuh).
 #pragma once
 #include <type_traits>
 #include "tc_pipeline.cuh"

@@ -1,7 +1,7 @@
 // tcgen05 engine for the implicit attention head (CIAOSR_ENGINE_TCGEN05), sm_100a.
 //
 // Persistent, warp-specialised kernels run every dense contraction of the head on the 5th-gen tensor
-// cores with fp32-grade accuracy (bf16 hi/lo split, 3 UMMAs per product, fp32 accumulation in TMEM):
+// cores with fp32-grade accuracy (fp16 hi/lo split, 3 UMMAs per product, fp32 accumulation in TMEM):
 //
 //   LR precompute     tc_gemm_kernel (gemm_tc.cuh): layer-1 hoists Pk, Pv and the key fold G
 //   pair_mlp_kernel   per 128 (query, neighbour) rows = 32 queries x 4 neighbours:
@@ -15,7 +15,7 @@
 // Pipeline (tc_pipeline.cuh): 1 CTA / SM, all 512 TMEM columns = two 128x256 fp32 accumulators; warp 0
 // streams pre-swizzled 16 KB weight slabs through a 4-stage ring with cp.async.bulk (TMA engine), warp 1
 // issues tcgen05.mma / tcgen05.commit, row threads drain accumulators with tcgen05.ld, apply bias+ReLU,
-// split to bf16 hi/lo and write the next layer's A operand straight into the 128B-swizzled K-major smem
+// split to fp16 hi/lo and write the next layer's A operand straight into the 128B-swizzled K-major smem
 // slabs the next UMMA reads.  Slab-granular mbarriers let layer l+1's UMMAs start as soon as the first 64
 // columns of layer l are converted, while the second accumulator absorbs them.  Hidden activations never
 // leave the SM.  In the two head kernels CTA pairs (2-CTA clusters) share one weight stream: each CTA

@@ -4,9 +4,9 @@
 // ciaosr_net.py:321-342).  cuDNN offers two ways to run its 146 convolutions: TF32 (10 ms for the bench
 // batch, but ~1e-3 relative error on the features, which the head turns into ~1e-3 output error: 10x the
 // parity tolerance) or fp32 CUDA cores (47 ms).  This file runs them as implicit GEMMs on tcgen05 with
-// bf16 hi/lo operand splits (fp32-grade results at tensor-core speed).
+// fp16 hi/lo operand splits (fp32-grade results at tensor-core speed).
 //
-// Layout: activations live in HBM as plain NHWC, two bf16 tensors (hi, lo) [B, H, W, C]; nothing is padded.
+// Layout: activations live in HBM as plain NHWC, two 16-bit tensors (hi, lo halves) [B, H, W, C]; nothing is padded.
 // One work tile = 16 rows x 8 columns of one image = 128 output pixels x 64 output channels.
 //
 // "Weights in tensor memory" formulation (convw).  Measured on B200 (profiles/r01e): a tcgen05.mma
@@ -24,9 +24,9 @@
 //                 start address that is not 1024-byte aligned needs nothing else (descriptor base offset 0;
 //                 measured: the other reading of the PTX text, base offset = row & 7, gives wrong sums);
 //   D[lane, col] = two accumulators of 128 columns: lanes 0-63 hold W_hi.X, lanes 64-127 hold W_lo.X with
-//                 X = X_hi + X_lo (all four bf16 products, 2 instructions per K16).
+//                 X = X_hi + X_lo (all four hi/lo products, 2 instructions per K16).
 // The epilogue transposes D through shared memory (out[pixel][c] = D[c][pixel] + D[64 + c][pixel] + bias),
-// applies residual / ReLU, splits to bf16 hi/lo and writes the next layer's buffers with 128-byte rows.
+// applies residual / ReLU, splits to fp16 hi/lo and writes the next layer's buffers with 128-byte rows.
 // Dense blocks never concatenate: every RDB owns one 576-channel buffer and each layer writes its 64
 // channels into its slice; the LFF output goes straight into the next block's buffer and the global
 // fusion buffer.  The residual trunk is kept in fp32.
@@ -52,7 +52,7 @@ struct ConvParams {
   int ntaps, cblocks;                  // 9 or 1; Cin / 64
   int half_bytes;                      // smem bytes of one (hi or lo) stage half, multiple of 1024
   int box_x;                           // columns of the TMA box (10 for 3x3, 8 for 1x1) = 8-row-group stride / 128
-  const uint8_t* wrows;                // per K-slab (cblock, tap): 128 rows [W_hi; W_lo] x 64 bf16 as [chunk of 8][row][8]
+  const uint8_t* wrows;                // per K-slab (cblock, tap): 128 rows [W_hi; W_lo] x 64 halves as [chunk of 8][row][8]
   const float* bias;                   // [64]
   const float* res32;                  // fp32 [B*H*W, 64] residual or nullptr
   int relu;
@@ -293,7 +293,7 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// ---- weight packing: conv weight [64, Cin, kh, kw] -> per K-slab (cblock, tap) 128 rows x 64 bf16 --------------
+// ---- weight packing: conv weight [64, Cin, kh, kw] -> per K-slab (cblock, tap) 128 rows x 64 halves -------------
 // chunk-major: [K-slab][16-byte chunk j = k / 8][row][k % 8], rows = [W_hi (64); W_lo (64)], so that the 32 rows
 // a stager warp loads with one instruction are 512 contiguous bytes
 constexpr int WSLAB_BYTES = 128 * 64 * 2;
@@ -339,7 +339,7 @@ struct Sfe1Src {          // B[n, k] = w[n*27 + k]
   const float* w;
   __device__ __forceinline__ float operator()(int, int n, int k) const { return w[n * 27 + k]; }
 };
-struct Sfe1Epi {          // + bias -> NHWC bf16 hi/lo + fp32
+struct Sfe1Epi {          // + bias -> NHWC fp16 hi/lo + fp32
   split_t* hi; split_t* lo; float* out32; const float* bias;
   __device__ __forceinline__ void store(const Sfe1Gen::Row&, long long g, int n0, const float (&v)[32]) const {
     if (n0 >= 64) return;

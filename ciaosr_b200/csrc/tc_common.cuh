@@ -11,8 +11,8 @@ namespace ciaosr {
 namespace tc {
 
 constexpr int ROWS = 128;            // UMMA M (one TMEM lane per row)
-constexpr int KSLAB = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int SLAB_BYTES = ROWS * 128;       // one [128 x 64] bf16 operand slab (SW128, K-major)
+constexpr int KSLAB = 64;            // 16-bit elements per 128-byte swizzle row
+constexpr int SLAB_BYTES = ROWS * 128;       // one [128 x 64] 16-bit operand slab (SW128, K-major)
 constexpr int UNIT_N = 128;          // weight rows per ring stage
 constexpr int UNIT_BYTES = 2 * SLAB_BYTES;   // hi slab + lo slab
 constexpr int HID = 256;

@@ -1,12 +1,12 @@
 // Shared pipeline of the tcgen05 kernels (head_tc.cu, gemm_tc.cuh): smem carve-up, mbarrier
 // protocol, weight producer, UMMA job issuer, accumulator drain helpers.
 //
-// One CTA per SM.  smem: 4 A-operand slots (bf16 hi + lo, [128 rows x 64 K] SW128 slabs), a 4-stage
+// One CTA per SM.  smem: 4 A-operand slots (fp16 hi + lo, [128 rows x 64 K] SW128 slabs), a 4-stage
 // ring of 16 KB weight slabs ([128 N x 64 K]; a weight "unit" = its hi slab then its lo slab),
 // 24 KB of per-kernel constants, 20 mbarriers.  TMEM: all 512 columns = two 128 x 256 fp32
 // accumulators D[0], D[1], used alternately by consecutive jobs.
 // A "job" = D[j&1][:, 0:128*units) = A[128, 64*nslabs] . W[128*units, 64*nslabs]^T evaluated as three
-// bf16 UMMAs per product term (A_lo.W_hi + A_hi.W_hi on the hi slab, A_hi.W_lo on the lo slab).
+// fp16 UMMAs per product term (A_lo.W_hi + A_hi.W_hi on the hi slab, A_hi.W_lo on the lo slab).
 //
 // Both column halves of an accumulator are produced by the same N = 256 UMMAs; the D_READY[d][half]
 // pair is committed together at the end of the job.
