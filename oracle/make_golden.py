@@ -97,6 +97,35 @@ def clip_case(name, c, hidden, h, w, scale, tile, overlap, seed=0):
          dict(lq=lq.numpy(), out=out.numpy()))
 
 
+def real_clip_case(name, c, hidden, h, w, scale, tile, overlap, seed=0):
+    """`RealCiaoSR.clip_test` (real_ciaosr.py:336-373) on a head without cross-scale attention.  The method is taken from the reference file by name (the module itself needs mmedit's GAN
+    classes at import time) and run unbound; its two `.cuda()` calls are made no-ops for the CPU run."""
+    import ast
+    src = "/root/reference/mmedited/models/restorers/real_ciaosr.py"
+    tree = ast.parse(open(src).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "RealCiaoSR")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "clip_test")
+    ns = {"torch": torch, "make_coord": rh.make_coord}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src, "exec"), ns)
+    # NB the reference's generator classes do not accept the extra keywords its own 002 configs pass
+    # (local_ensemble_coord, imnet_k_type, imnet_v_type, res, cat_nla_v -> TypeError at this commit), so the only
+    # 002 head flag that can be exercised against the reference is non_local_attn=False; the residual stays on.
+    g = rh.build_reference_generator("edsr", c, hidden, num_blocks=1, eval_bsize=500, non_local_attn=False)
+    synth.fill_module(g, seed)
+    lq = synth.synth_lr_image(1, h, w, seed)
+    fake_self = types.SimpleNamespace(test_cfg=dict(scale=scale, tile=tile, tile_overlap=overlap))
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            out = ns["clip_test"](fake_self, lq, g)
+    finally:
+        torch.Tensor.cuda = saved
+    save(name, dict(kind="clip_real", c=c, hidden=list(hidden), h=h, w=w, scale=scale, tile=tile, overlap=overlap,
+                    seed=seed, eval_bsize=500, non_local=False),
+         dict(lq=lq.numpy(), out=out.numpy()))
+
+
 def swinir_case(name, shapes, seed=0, **kw):
     """The SwinIR trunk (gen_feature) of the reference generator, with the reference's state_dict
     keys and shapes recorded so that checkpoint compatibility is pinned too."""
@@ -146,6 +175,7 @@ def main():
     csattn_case("csattn_odd", 16, 2, 9, 11, seed=8)
     # tiled inference through the restorer
     clip_case("clip_small", 16, (32, 32), 40, 36, 2, 24, 8, seed=9)
+    real_clip_case("clip_real_small", 16, (32, 32), 30, 44, 4, 16, 4, seed=15)
     # SwinIR trunk: window-multiple size (buffered shift mask), padded sizes (reflect pad + recomputed mask)
     swinir_case("swinir_trunk", [(1, 8, 8), (2, 10, 13), (1, 16, 12)], seed=10,
                 embed_dim=24, depths=(2, 2), num_heads=(2, 2), window_size=4, img_size=8, mlp_ratio=2)

@@ -71,20 +71,28 @@ def test_head_golden(name):
                 assert max_abs(pred2, a[f"pred_{tag}"]) < TOL, (engine, tag, "injected")
 
 
-def test_clip_test_golden():
+@pytest.mark.parametrize("name", ["clip_small", "clip_real_small"])
+def test_clip_test_golden(name):
+    """CiaoSR.clip_test (ciaosr.py:218-258) / RealCiaoSR.clip_test (real_ciaosr.py:336-373, through the EMA
+    generator) against the frames the reference's own methods produced."""
     from ciaosr_b200.builder import build
-    from ciaosr_b200.restorers import CiaoSR
+    from ciaosr_b200.restorers import CiaoSR, RealCiaoSR
     from tests.util import generator_cfg
-    meta, a = load_case("clip_small")
+    meta, a = load_case(name)
     dev = _dev()
-    m = build(dict(type=CiaoSR, generator=generator_cfg(meta["c"], meta["hidden"], meta["eval_bsize"]),
+    real = meta["kind"] == "clip_real"
+    m = build(dict(type=RealCiaoSR if real else CiaoSR,
+                   generator=generator_cfg(meta["c"], meta["hidden"], meta["eval_bsize"],
+                                           non_local=meta.get("non_local", True)),
                    pixel_loss=dict(type="L1Loss"), rgb_mean=(0.4488, 0.4371, 0.4040),
                    rgb_std=(1., 1., 1.)),
               test_cfg=dict(scale=meta["scale"], tile=meta["tile"], tile_overlap=meta["overlap"]))
     synth.fill_module(m.generator, meta["seed"])
+    if real:
+        m.generator_ema.load_state_dict(m.generator.state_dict())
     m = m.eval().to(dev)
     with torch.no_grad():
-        out = m.clip_test(a["lq"].to(dev), m.generator).cpu()
+        out = m.clip_test(a["lq"].to(dev), m._test_generator()).cpu()
     assert out.shape == a["out"].shape
     assert max_abs(out, a["out"]) < TOL
 

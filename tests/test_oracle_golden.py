@@ -49,18 +49,21 @@ def test_make_coord_matches_fixture():
     assert torch.equal(orc.cell_for((th, tw), th * tw), a["cell_s2"][0])
 
 
-def test_clip_test():
-    meta, a = load_case("clip_small")
+@pytest.mark.parametrize("name", ["clip_small", "clip_real_small"])      # CiaoSR.clip_test / RealCiaoSR.clip_test
+def test_clip_test(name):
+    meta, a = load_case(name)
     g = build_generator(dict(c=meta["c"], hidden=meta["hidden"], eval_bsize=meta["eval_bsize"],
-                             seed=meta["seed"]))
+                             seed=meta["seed"], non_local=meta.get("non_local", True)))
     w = head_weights(g)
 
     def model(patch, coord, cell):
         with torch.no_grad():
             feat = g.gen_feature(patch)[0]
-        return orc.head_forward(patch, feat, coord, cell, w, eval_bsize=meta["eval_bsize"])
+        return orc.head_forward(patch, feat, coord, cell, w, eval_bsize=meta["eval_bsize"],
+                                non_local_attn=meta.get("non_local", True))
 
     out = orc.clip_test(a["lq"], model, meta["scale"], meta["tile"], meta["overlap"])
+    assert out.shape == a["out"].shape
     assert max_abs(out, a["out"]) < TOL
 
 
