@@ -105,3 +105,40 @@ def test_no_cpu_fallback(lib):
     assert rc == _lib.E_NO_DEVICE
     with pytest.raises(_lib.CiaoSRNativeError):
         _lib.check(rc)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in ciaosr_b200/_lib.py against the C compiler's view of include/ciaosr_b200.h
+    (the header is plain C: compile a probe with gcc and compare sizes and field offsets)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    probes = {
+        "ciaosr_mlp_desc": (_lib.MlpDesc, ["n_layers", "dims", "weight", "bias"]),
+        "ciaosr_cs_attn_desc": (_lib.CsAttnDesc, ["channels", "n_scales", "scales", "softmax_scale", "match1_w",
+                                                  "match2_slope", "assembly_w", "down_w", "down_b", "escape_nan"]),
+        "ciaosr_head_desc": (_lib.HeadDesc, ["abi_version", "channels", "feat_unfold", "local_size",
+                                             "non_local_attn", "softmax_scale", "imnet_q", "imnet_k", "imnet_v",
+                                             "cs_attn"]),
+        "ciaosr_rdn_desc": (_lib.RdnDesc, ["abi_version", "mid_channels", "num_layers", "sfe1_w", "sfe2_b",
+                                           "dense_w", "lff_b", "gff0_w", "gff1_b"]),
+        "ciaosr_linear_desc": (_lib.LinearDesc, ["abi_version", "in_features", "out_features", "weight", "bias"]),
+    }
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ciaosr_b200.h"', "int main(void) {"]
+    for cname, (_, fields) in probes.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  printf("CIAOSR_N_STAGES %d\\n", CIAOSR_N_STAGES);', "  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, (ctype, fields) in probes.items():
+        assert int(got[cname]) == ctypes.sizeof(ctype), cname
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(ctype, f).offset, (cname, f)
+    assert int(got["CIAOSR_N_STAGES"]) == _lib.N_STAGES == len(_lib.STAGE_NAMES)
