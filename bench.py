@@ -15,8 +15,20 @@ restorer call a user makes (`model(lq, test_mode=True, coord=, cell=)`, ciaosr.p
 from pinned host buffers, result back on the host.  N > 1: weak scaling, every rank runs its
 own batch and the ranks all-gather the final RGB (the only collective on the path).
 
-`--impl reference` times the reference's algorithm on the host CPU (the oracle port of it;
-the reference itself needs mmcv/mmedit and cannot be installed) on a bounded sample.
+The line also carries (rank 0):
+  parity      max-abs of the very output that was timed against (a) the frames the UNMODIFIED reference produced
+              for crops 0 and 1 of this batch (tests/golden/full_cfg2.npz, minted by oracle/make_golden_full.py)
+              and (b) the CPU leg's output for crop 0, computed in this process; tolerance 1e-4
+  strong      N > 1: ONE batch of 16 crops split over the ranks (dist.sharded_batch_forward), Mpix/s of that one
+              batch and its bit-equality with the batch a rank computes alone
+  other_configs  BASELINE.json configs 3 (x4 tiled), 4 and 5 at full size through the restorer's tiled inference
+              (tools/run_configs.py), tiles sharded over the ranks when N > 1 (strong scaling of one frame), each
+              with its bit-equality against the single-rank frame
+
+`--impl reference` times the UNMODIFIED reference (its LocalImplicitSRRDN.forward with the stock batched_predict,
+imported through oracle/ref_harness.py's stubs from /root/reference or the runtime copy baseline/_ref that
+__graft_entry__.build() makes) on the host CPU, two crops of the batch per step; if that copy is absent it falls
+back to the oracle port and says so (`cpu_baseline.kind`).
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -171,45 +183,91 @@ def cpu_threads():
     return int(os.environ.get("CIAOSR_CPU_THREADS", min(os.cpu_count() or 1, 16)))
 
 
-def cpu_reference_sample(steps, warmup, threads):
-    """The reference's algorithm on host cores: RDN encoder (torch CPU) + oracle head with
-    the reference's eval_bsize chunking (cross-scale attention recomputed per chunk)."""
-    from oracle import ciaosr_oracle as orc
+def reference_generator():
+    """The UNMODIFIED reference's LocalImplicitSRRDN (RDN 16x8, imnet 256x4, cross-scale attention) with the same
+    synthetic weights as our model, or None when no copy of the reference is available on this box."""
+    try:
+        from ciaosr_b200 import synth
+        from oracle import ref_harness as rh
+        if not rh.reference_available():
+            return None
+        g = rh.build_reference_generator("rdn", C, tuple(HIDDEN), num_blocks=16, num_layers=8, eval_bsize=EVAL_BSIZE)
+        synth.fill_module(g, 0)
+        return g
+    except Exception as e:                                     # noqa: BLE001 -- fall back to the port, loudly
+        log(f"reference import failed ({type(e).__name__}: {e}); falling back to the oracle port")
+        return None
+
+
+def cpu_reference_sample(steps, warmup, threads, crops=1, seed=100):
+    """The reference's own CPU implementation of the path on host cores, on the first `crops` crops of the batch
+    `make_inputs(B, seed)` (= rank 0's batch): kind "reference" = the unmodified reference module (forward with
+    test_mode=True: RDN encoder + stock batched_predict, cross-scale attention recomputed per eval_bsize chunk);
+    kind "port" = the same encoder in torch-CPU + the oracle restatement of the head with the same chunking.
+    Returns (Mpix/s, ms per step, kind, output [crops, Q, 3])."""
     torch.set_num_threads(threads)
-    m = build_model()
-    g = m.generator
-    w = {k: v.detach() for k, v in g.state_dict().items()}
-    lq, coord, cell = make_inputs(1, 1)
-    lq = lq - torch.tensor(RGB_MEAN).view(1, 3, 1, 1)
+    lq, coord, cell = make_inputs(B, seed)
+    lq = (lq - torch.tensor(RGB_MEAN).view(1, 3, 1, 1))[:crops].contiguous()
+    coord, cell = coord[:crops].contiguous(), cell[:crops].contiguous()
+    ref = reference_generator()
+    if ref is not None:
+        kind = "reference"
+
+        def run():
+            return ref(lq, coord, cell, test_mode=True)
+    else:
+        from oracle import ciaosr_oracle as orc
+        kind = "port"
+        g = build_model().generator
+        w = {k: v.detach() for k, v in g.state_dict().items()}
+
+        def run():
+            outs = []
+            for i in range(crops):
+                feat = g.gen_feature(lq[i:i + 1])[0]
+                outs.append(orc.head_forward(lq[i:i + 1], feat, coord[i:i + 1], cell[i:i + 1], w, eval_bsize=EVAL_BSIZE))
+            return torch.cat(outs, 0)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            feat = g.gen_feature(lq)[0]
-            out = orc.head_forward(lq, feat, coord, cell, w, eval_bsize=EVAL_BSIZE)
+            out = run()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    assert out.shape == (1, H * SCALE * W * SCALE, 3)
-    px = H * SCALE * W * SCALE
+    px = crops * H * SCALE * W * SCALE
+    assert out.shape == (crops, H * SCALE * W * SCALE, 3)
     mean = sum(times) / len(times)
-    return px / mean / 1e6, mean * 1e3
+    return px / mean / 1e6, mean * 1e3, kind, out
+
+
+def workload_config(world):
+    """The static description of the workload: identical in both arms' lines."""
+    return {"workload": "RDN-CiaoSR config 001 (RDN 16x8 g64, imnet 256x4, cs_attn), "
+                        "batch 16 of 48x48 LR -> x4, per GPU",
+            "px_per_step_per_gpu": B * H * SCALE * W * SCALE, "eval_bsize": EVAL_BSIZE,
+            "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = cpu_threads()
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    val, ms = cpu_reference_sample(steps, warmup, threads)
-    sample = f"1 of the {B} LR 48x48 crops -> x4 (36 864 px) per step, {steps} steps"
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    crops = 2
+    val, ms, kind, _ = cpu_reference_sample(steps, warmup, threads, crops=crops)
+    sample = (f"crops 0-{crops - 1} of the {B} LR 48x48 crops -> x4 ({crops * H * SCALE * W * SCALE} px) per step, "
+              f"{steps} timed steps; Mpix/s of the sample = Mpix/s of the batch (crops are independent forwards of "
+              f"equal cost: the batch-16 step would take {B // crops}x as long)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "RDN-CiaoSR config 001, 48x48 -> x4, CPU sample of the batch-16 workload",
-                   "eval_bsize": EVAL_BSIZE, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": kind, "sample": sample,
+                         "what": ("unmodified reference (mmedited LocalImplicitSRRDN.forward, stock batched_predict) "
+                                  "through oracle/ref_harness.py stubs" if kind == "reference" else
+                                  "oracle port of the reference's algorithm (no copy of the reference on this box)")},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -238,6 +296,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--other-configs", default="3,4,5",
+                    help="BASELINE.json configs to run once at full size after the timed workload ('' = none)")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the generator forward as a CUDA graph")
     ap.add_argument("--channels-last", type=int, default=1, help="PyTorch encoder in channels_last")
     ap.add_argument("--native-encoder", type=int, default=1, help="RDN encoder on the native tcgen05 path")
@@ -368,6 +428,63 @@ def main():
     ms_enc = ms_eager - ms_head
     log(f"eager step {ms_eager:.2f} ms, head {ms_head:.2f} ms, e2e {ms_e2e:.2f} ms")
 
+    # ---- the output that was timed, for the parity block (rank 0's batch = seed 100 = the golden's batch) ----------
+    with torch.no_grad():
+        out_timed = step_device().detach().clone()
+    torch.cuda.synchronize()
+
+    # ---- strong scaling of ONE batch (N > 1): every rank holds rank 0's batch, each runs 16/N crops ------------------
+    strong = None
+    if world > 1:
+        from ciaosr_b200 import dist as cdist
+        lq0_h, _, _ = make_inputs(B, 100)
+        lq0 = (lq0_h - torch.tensor(RGB_MEAN).view(1, 3, 1, 1)).to(dev)
+
+        def step_strong():
+            with torch.no_grad():
+                return cdist.sharded_batch_forward(gen, lq0, coord_d, cell_d)
+        for _ in range(3):
+            step_strong()
+        ms_strong, _, _ = timed(step_strong, args.steps)
+        with torch.no_grad():
+            alone = gen(lq0, coord_d, cell_d, test_mode=True)
+            diff = float((step_strong() - alone).abs().max())
+        strong = {"what": "ONE batch of 16 crops split over the ranks (16/N crops each), one all-gather of the RGB",
+                  "value": npx / (ms_strong * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms_strong,
+                  "max_abs_vs_single_rank": diff, "bit_equal": diff == 0.0}
+        log(f"strong scaling of one batch: {ms_strong:.2f} ms")
+
+    # ---- BASELINE.json configs 3 / 4 / 5 at full size (one frame each; tiles sharded over the ranks) -----------------
+    other = []
+    if args.other_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs as rc
+        want = {int(c) for c in args.other_configs.split(",") if c}
+        for case in rc.cases(want):
+            if case["config"] == 3 and case["scale"] not in (4, 8):
+                continue
+            rec = {"config": case["config"], "case": case["name"], "n_gpus": world}
+            try:
+                m2, gen2, lq2, kw2, tcfg2, fstd = rc.prepare(case, dev)
+                rc.run_frame(m2, lq2, kw2, world)                      # warm-up: plans, graphs per tile shape
+                ms2, _, _ = timed(lambda: rc.run_frame(m2, lq2, kw2, world), 2)
+                frame = rc.run_frame(m2, lq2, kw2, world)
+                px2 = case["h"] * case["scale"] * case["w"] * case["scale"]
+                rec.update(hr_px=px2, ms=ms2, mpix_s=px2 / ms2 / 1e3, finite=bool(torch.isfinite(frame).all()),
+                           sharding=("none" if world == 1 else
+                                     "tiles round-robin over ranks + one all-gather" if tcfg2.get("tile") else
+                                     "bands of the coordinate list over ranks + one all-gather"),
+                           synthetic_feature_std=fstd)
+                if world > 1:
+                    d2 = float((rc.run_alone(m2, lq2, kw2) - frame).abs().max())
+                    rec.update(max_abs_vs_single_rank=d2, bit_equal=d2 == 0.0)
+                del m2, gen2, frame
+            except Exception as e:                                     # noqa: BLE001 -- never lose the headline line
+                rec["error"] = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.empty_cache()
+            log(f"config {case['config']} {case['name']}: {rec.get('ms', float('nan')):.1f} ms {rec.get('error', '')}")
+            other.append(rec)
+
     if rank == 0:
         from oracle.ciaosr_oracle import cross_scale_flops, head_flops_per_query
         pk = peaks()
@@ -386,16 +503,15 @@ def main():
                 "algorithmic_flops_per_px": fl_head - fl_q, "ms_per_step": pair_ms,
                 "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                 "hbm_algorithmic_GBps": 61.0 * npx / (ms_head * 1e-3) / 1e9, "hbm_peak_GBps": pk["hbm_gbs"]}
+        cfg = workload_config(world)
+        cfg["engine"] = engine
         line = {
             "metric": METRIC, "value": world * npx / (ms_step * 1e-3) / 1e6, "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "RDN-CiaoSR config 001 (RDN 16x8 g64, imnet 256x4, cs_attn), "
-                                   "batch 16 of 48x48 LR -> x4, per GPU",
-                       "px_per_step_per_gpu": npx, "eval_bsize": EVAL_BSIZE, "engine": engine,
-                       "l2": "256 MiB flush between timed steps", "parallelism": f"dp{world} + all-gather of RGB",
-                       "head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
+            "config": cfg,
+            "detail": {"head_only_mpix_s": world * npx / (ms_head * 1e-3) / 1e6,
                        "head_ms": ms_head, "eager_step_ms": ms_eager, "encoder_ms_est": ms_enc,
                        "encoder": ("native RDN on tcgen05 (fp16 hi/lo split implicit GEMM, fp32-grade; csrc/rdn_tc.cu)"
                                    if getattr(gen, "native_encoder", False) else
@@ -408,12 +524,28 @@ def main():
             "gpu_launches": launches,
             "roofline": roof,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if other:
+            line["other_configs"] = other
+        # parity of the timed output: against the frames the unmodified reference produced for these very crops
+        parity = {"tolerance": 1e-4}
+        gpath = os.path.join(ROOT, "tests", "golden", "full_cfg2.npz")
+        if os.path.exists(gpath):
+            import numpy as np
+            gold = torch.from_numpy(np.load(gpath)["out"])
+            parity["max_abs_vs_reference_golden"] = float((out_timed[:gold.shape[0]].cpu() - gold).abs().max())
+            parity["golden"] = "tests/golden/full_cfg2.npz (crops 0-1, unmodified reference on CPU)"
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()
-            val, ms = cpu_reference_sample(5, 1, threads)
-            log(f"cpu baseline done: {ms:.0f} ms per sample on {threads} threads")
-            line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
-                                    "sample": "1 of the 16 crops (36 864 px), 5 timed runs, %.0f ms each" % ms}
+            val, ms, kind, cpu_out = cpu_reference_sample(3, 1, threads, crops=1)
+            log(f"cpu baseline ({kind}) done: {ms:.0f} ms per sample on {threads} threads")
+            line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": threads, "kind": kind,
+                                    "sample": "crop 0 of the 16 crops (36 864 px), 3 timed runs, %.0f ms each" % ms}
+            parity["max_abs_vs_cpu_leg"] = float((out_timed[:1].cpu() - cpu_out).abs().max())
+        errs = [v for k, v in parity.items() if k.startswith("max_abs")]
+        parity["ok"] = bool(errs) and max(errs) < parity["tolerance"]
+        line["parity"] = parity
         emit(line)
     if world > 1:
         dist.destroy_process_group()

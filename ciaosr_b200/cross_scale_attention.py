@@ -31,7 +31,15 @@ class CrossScaleAttention(nn.Module):
         if 4 in self.scale:
             self.downx4 = nn.Conv2d(channel, channel, ksize, 4, 1)
         self.down = nn.Conv2d(channel, channel, ksize, 2, 1)
-        self._plan = None
+
+    @property
+    def _plan(self):
+        """(parameter versions, CsAttnOnlyPlan) of the standalone path; held outside the module (native.module_cache)."""
+        return native.module_cache(self).get("plan")
+
+    @_plan.setter
+    def _plan(self, value):
+        native.module_cache(self)["plan"] = value
 
     def forward(self, x):
         """[B,C,H,W] -> [B, C*len(scale), H, W]; standalone use (inside the head the

@@ -45,6 +45,28 @@ extern std::atomic<long long> g_launch_count;
     }                                                                            \
   } while (0)
 
+// ---- opt-in to > 48 KB of dynamic shared memory --------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (function, DEVICE): a process that uses
+// cuda:1 after cuda:0 must opt in again there.  One DynSmemOptIn per kernel remembers, per device, the
+// largest size already granted; concurrent callers may both set the attribute (harmless, same value).
+constexpr int CIAOSR_MAX_DEVICES = 64;
+struct DynSmemOptIn {
+  std::atomic<int> granted[CIAOSR_MAX_DEVICES] = {};
+  template <class Kernel>
+  int ensure(Kernel kernel, int bytes) {
+    int dev = 0;
+    CIAOSR_CUDA_OK(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < CIAOSR_MAX_DEVICES;
+    if (tracked && granted[dev].load(std::memory_order_acquire) >= bytes) return CIAOSR_OK;
+    CIAOSR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (tracked) {
+      int cur = granted[dev].load(std::memory_order_relaxed);
+      while (cur < bytes && !granted[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+    }
+    return CIAOSR_OK;
+  }
+};
+
 // ---- stage timing ---------------------------------------------------------
 struct StageScope {          // RAII: records an event pair around a stage when profiling is on
   int stage; cudaStream_t st; cudaEvent_t a, b; bool on;

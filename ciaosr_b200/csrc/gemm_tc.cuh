@@ -178,12 +178,8 @@ static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, co
   if (g.M <= 0) return CIAOSR_OK;
   CIAOSR_REQUIRE(!agen_tma<AGen>::value || (map_hi && map_lo), CIAOSR_E_INVALID, "tc_gemm: tensor maps missing");
   static const CUtensorMap no_map = {};
-  static bool attr_set = false;      // one per template instantiation
-  if (!attr_set) {
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<AGen, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SM_TOTAL));
-    attr_set = true;
-  }
+  static DynSmemOptIn optin;         // one per template instantiation, per device (common.cuh)
+  if (int rc = optin.ensure(tc_gemm_kernel<AGen, Epi>, SM_TOTAL)) return rc;
   const long long n_jobs = ((g.M + ROWS - 1) / ROWS) * ((g.nunits + 1) / 2);
   if (g.kchunk > 0 && g.kchunk < g.kslabs) {
     const bool can = epi_accumulates<Epi, typename AGen::Row>::value;

@@ -376,14 +376,10 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     if ((rc = run_lr_precompute_tc(L, plan, a, b.Pk, b.Pv, b.G, tc_ldg(), st))) return rc;
   }
   const int CL = tc_cluster_size();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(pair_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(pair_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(query_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(query_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    attr_set = true;
-  }
+  static DynSmemOptIn optin[4];       // per kernel, per device (common.cuh)
+  if ((rc = optin[0].ensure(pair_mlp_kernel<1>, SM_TOTAL)) || (rc = optin[1].ensure(pair_mlp_kernel<2>, SM_TOTAL)) ||
+      (rc = optin[2].ensure(query_mlp_kernel<1>, SM_TOTAL)) || (rc = optin[3].ensure(query_mlp_kernel<2>, SM_TOTAL)))
+    return rc;
   const long long total_q = (long long)a.B * a.Q;
   {
     StageScope sc(3, st);

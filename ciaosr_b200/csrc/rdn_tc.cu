@@ -457,11 +457,8 @@ static int launch_convw(ConvParams P, const MapPair& mp, cudaStream_t st) {
   const int box_y = P.ntaps == 9 ? TILE_Y + 2 : TILE_Y;
   P.half_bytes = (P.box_x * box_y * 128 + 1023) / 1024 * 1024;
   const int smem_bytes = 2 * CW_A_STAGES * P.half_bytes + CW_FIXED_BYTES;
-  static int max_set = 0;
-  if (smem_bytes > max_set) {
-    CIAOSR_CUDA_OK(cudaFuncSetAttribute(convw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    max_set = smem_bytes;
-  }
+  static DynSmemOptIn optin;          // per device (common.cuh)
+  if (int rc = optin.ensure(convw_tc_kernel, smem_bytes)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tc_grid_size(P.n_tiles)); cfg.blockDim = dim3(CW_THREADS);
   cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;

@@ -47,7 +47,6 @@ class LocalImplicitSRNet(nn.Module):
         # run the encoder convolutions in channels_last (cuDNN's native layout; saves the NCHW<->NHWC passes)
         self.cuda_graph = cuda_graph
         self.channels_last = channels_last
-        self._graphs = {}
         if not local_ensemble_coord:
             raise NotImplementedError("local_ensemble_coord=False has no counterpart in the reference head")
 
@@ -72,8 +71,33 @@ class LocalImplicitSRNet(nn.Module):
         self.imnet_v = build_component(imnet_v)
         if non_local_attn:
             self.cs_attn = CrossScaleAttention(channel=imnet_dim, scale=self.multi_scale)
-        self._plan = None
-        self._plan_key = None
+
+    # -- native state ----------------------------------------------------------------
+    # Packed plans and CUDA graphs are kept outside the module (native.module_cache): they hold ctypes structs and
+    # device pointers, which must not travel through copy.deepcopy / pickle (EMA copies, torch.save(model)).
+    def _nc(self):
+        return native.module_cache(self)
+
+    @property
+    def _plan(self):
+        return self._nc().get("plan")
+
+    @property
+    def _graphs(self):
+        return self._nc().setdefault("graphs", {})
+
+    def _native_buffers(self):
+        """Every device buffer the library was handed on behalf of this module right now: packed plans and their
+        current workspaces.  A captured CUDA graph addresses them by raw pointer, so each graph entry holds these
+        references: a later, larger call may replace a plan's workspace (or a parameter update its packed buffer),
+        but the blocks an existing graph replays into stay allocated for as long as that graph does."""
+        keep = []
+        for m in self.modules():
+            for v in native.module_cache(m).values():
+                plan = v[1] if isinstance(v, tuple) and len(v) == 2 else v
+                if isinstance(plan, (native.HeadPlan, native.RdnPlan, native.LinearPlan)):
+                    keep += [plan, plan.buf, getattr(plan, "_ws", None)]
+        return keep
 
     # -- native plan -----------------------------------------------------------------
     def _head_params(self):
@@ -84,14 +108,15 @@ class LocalImplicitSRNet(nn.Module):
         """Packed weights for the kernels; rebuilt when a parameter changes or moves."""
         params = self._head_params()
         key = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in params.items())
-        if self._plan is None or key != self._plan_key:
-            self._plan = native.HeadPlan(
+        nc = self._nc()
+        if nc.get("plan") is None or key != nc.get("plan_key"):
+            nc["plan"] = native.HeadPlan(
                 params, self.imnet_dim, local_size=self.local_size,
                 non_local_attn=self.non_local_attn, multi_scale=self.multi_scale,
                 softmax_scale=float(self.softmax_scale), feat_unfold=self.feat_unfold,
                 cs_softmax_scale=float(self.cs_attn.softmax_scale) if self.non_local_attn else 10.0)
-            self._plan_key = key
-        return self._plan
+            nc["plan_key"] = key
+        return nc["plan"]
 
     # -- reference API -----------------------------------------------------------------
     def forward(self, x, coord, cell, test_mode=False):
@@ -115,9 +140,10 @@ class LocalImplicitSRNet(nn.Module):
     def _forward_graphed(self, x, coord, cell, test_mode):
         """One CUDA graph per (shapes, test_mode); inputs are copied into static buffers and the
         static output is cloned, so callers see ordinary tensors."""
-        # head weights are packed into the plan: a new graph is needed when any of them changes
-        sig = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
-                    if n.startswith(("imnet_", "cs_attn.")))
+        # Head AND encoder weights are packed into plans (HeadPlan, RdnPlan, one LinearPlan per trunk Linear) that the
+        # captured kernels address directly: a new graph is needed when ANY parameter or buffer changes or moves
+        # (load_state_dict, init_weights, an in-place update), not only the head's.
+        sig = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         key = (tuple(x.shape), tuple(coord.shape), bool(test_mode), x.device.index, sig)
         entry = self._graphs.get(key)
         if entry is None:
@@ -131,11 +157,12 @@ class LocalImplicitSRNet(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 so = self._forward_eager(sx, sc, sl, test_mode)
-            entry = (graph, sx, sc, sl, so)
+            # the plans / workspaces this capture recorded pointers of stay alive with the graph (_native_buffers)
+            entry = (graph, sx, sc, sl, so, self._native_buffers())
             if len(self._graphs) >= 8:                         # bound the pools kept alive
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = entry
-        graph, sx, sc, sl, so = entry
+        graph, sx, sc, sl, so = entry[:5]
         sx.copy_(x, non_blocking=True)
         sc.copy_(coord, non_blocking=True)
         sl.copy_(cell, non_blocking=True)
@@ -184,18 +211,17 @@ class LocalImplicitSRRDN(LocalImplicitSRNet):
         # 'auto' uses it for CUDA inputs when the geometry admits it (mid_channels == growth == 64);
         # False keeps the PyTorch / cuDNN encoder of the reference.
         self.native_encoder = "auto"
-        self._enc_plan = None
-        self._enc_key = None
 
     def _native_encoder_plan(self):
         names = ("sfe1.", "sfe2.", "rdbs.", "gff.")
         params = {k: v for k, v in self.state_dict().items() if k.startswith(names)}
         key = tuple((k, v.data_ptr(), v._version) for k, v in params.items())
-        if self._enc_plan is None or key != self._enc_key:
+        nc = self._nc()
+        if nc.get("enc_plan") is None or key != nc.get("enc_key"):
             mid, growth, nb, nl = self._enc_geom
-            self._enc_plan = native.RdnPlan(params, mid, growth, nb, nl)
-            self._enc_key = key
-        return self._enc_plan
+            nc["enc_plan"] = native.RdnPlan(params, mid, growth, nb, nl)
+            nc["enc_key"] = key
+        return nc["enc_plan"]
 
     def gen_feature(self, x):
         mid, growth = self._enc_geom[:2]

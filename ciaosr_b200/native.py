@@ -5,11 +5,25 @@ workspace, outputs) and provides the current CUDA stream.  All arithmetic of
 the hot path happens inside ``libciaosr_b200.so``.
 """
 import ctypes
+import weakref
 
 import torch
 
 from . import _lib
 from ._lib import CiaoSRNativeError, ENGINES  # noqa: F401  (re-exported)
+
+
+# Per-module native state (packed plans, CUDA graphs) lives OUTSIDE the nn.Module, keyed weakly on it: the plans hold
+# ctypes structs with pointers, which copy.deepcopy / pickle / torch.save(model) cannot pass through.  A copied or
+# unpickled module simply starts with an empty cache and rebuilds its plans lazily from its own parameters.
+_MODULE_CACHE = weakref.WeakKeyDictionary()
+
+
+def module_cache(module):
+    d = _MODULE_CACHE.get(module)
+    if d is None:
+        d = _MODULE_CACHE[module] = {}
+    return d
 
 
 def _ptr(t):

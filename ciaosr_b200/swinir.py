@@ -58,10 +58,10 @@ def _linear(x, lin, gelu=False):
         from . import native
         if native.LinearPlan.supports(w):
             key = (w.data_ptr(), w._version, None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
-            cache = lin.__dict__.get("_native_plan")
+            mc = native.module_cache(lin)             # not in lin.__dict__: keeps the module deepcopy- / pickle-able
+            cache = mc.get("linear_plan")
             if cache is None or cache[0] != key:
-                cache = (key, native.LinearPlan(w, lin.bias))
-                lin.__dict__["_native_plan"] = cache
+                cache = mc["linear_plan"] = (key, native.LinearPlan(w, lin.bias))
             return cache[1].forward(x, gelu=gelu)
     y = lin(x)
     return F.gelu(y) if gelu else y

@@ -38,7 +38,22 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("CIAOSR_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_root():
+    """Where the unmodified reference package lies: the mounted checkout in the build container, else the
+    runtime copy `__graft_entry__.build()` places under baseline/_ref (git-ignored; it travels to the GPU box so
+    that `bench.py --impl reference` can time the reference itself there)."""
+    if os.environ.get("CIAOSR_NO_REFERENCE"):              # tests: exercise the "no copy of the reference" path
+        return os.environ.get("CIAOSR_REFERENCE_ROOT", "/nonexistent")
+    for cand in (os.environ.get("CIAOSR_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "mmedited")):
+            return cand
+    return os.environ.get("CIAOSR_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available():
@@ -248,7 +263,7 @@ def import_reference():
 
 def build_reference_generator(kind="edsr", mid_channels=64, hidden=(256, 256, 256, 256),
                               num_blocks=2, eval_bsize=None, local_size=2,
-                              non_local_attn=True, softmax_scale=1):
+                              non_local_attn=True, softmax_scale=1, num_layers=2):
     """Instantiate the reference's generator class with a small encoder."""
     ref = import_reference()
     mlp_cfg = lambda: dict(type="MLPRefiner", in_dim=4, out_dim=3,
@@ -261,7 +276,7 @@ def build_reference_generator(kind="edsr", mid_channels=64, hidden=(256, 256, 25
         cls = ref.net.LocalImplicitSRRDN
         enc = dict(type="RDN", in_channels=3, out_channels=3,
                    mid_channels=mid_channels, num_blocks=num_blocks,
-                   upscale_factor=4, num_layers=2, channel_growth=mid_channels)
+                   upscale_factor=4, num_layers=num_layers, channel_growth=mid_channels)
     else:
         raise ValueError(kind)
     gen = cls(encoder=enc, imnet_q=mlp_cfg(), imnet_k=mlp_cfg(), imnet_v=mlp_cfg(),

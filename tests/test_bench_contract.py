@@ -22,8 +22,22 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 4
+    # the unmodified reference when a copy is on this box (/root/reference or baseline/_ref), else the oracle port
+    from oracle import ref_harness as rh
+    assert d["cpu_baseline"]["kind"] == ("reference" if rh.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] == 4
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    import bench
+    assert d["config"] == bench.workload_config(1)            # the same static config dict as our arm's line
+
+
+def test_reference_arm_falls_back_to_the_port_without_a_reference_copy(tmp_path):
+    env = dict(os.environ, CIAOSR_CPU_THREADS="4", CIAOSR_REFERENCE_ROOT=str(tmp_path), CIAOSR_NO_REFERENCE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

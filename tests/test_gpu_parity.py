@@ -494,3 +494,149 @@ def test_full_size_models_engines_agree(config):
     assert a.shape == (1, 3, 4 * n, 4 * n) and torch.isfinite(a).all()
     assert 0.02 < float(a.std())
     assert max_abs(a, b) < TOL
+
+
+# ---- BASELINE-size parity against reference-minted goldens (oracle/make_golden_full.py) ---------------------------
+def _bench_model(dev, native_encoder="auto", engine="auto"):
+    import bench
+    m = bench.build_model(engine).to(dev)
+    m.generator.native_encoder = native_encoder
+    return bench, m
+
+
+@pytest.mark.parametrize("engine,native_enc", [("tcgen05", "auto"), ("simt", False)])
+def test_config2_end_to_end_golden(engine, native_enc):
+    """BASELINE.json config 2 exactly as bench.py times it (RDN 16x8 + head, 48x48 -> x4, eval_bsize 30000), crops
+    0 and 1 of rank 0's batch, against the UNMODIFIED reference's forward (CPU fp32): the product path (native
+    tcgen05 encoder + tcgen05 head) and the all-fp32 path both within the 1e-4 tolerance."""
+    dev = _dev()
+    meta, a = load_case("full_cfg2")
+    bench, m = _bench_model(dev, native_enc, engine)
+    lq, coord, cell = bench.make_inputs(16, meta["seed"])
+    lq = (lq - torch.tensor(bench.RGB_MEAN).view(1, 3, 1, 1))[:2].contiguous().to(dev)
+    g = m.generator
+    with torch.no_grad():
+        feat = g.gen_feature(lq)[0]
+        out = g(lq, coord[:2].contiguous().to(dev), cell[:2].contiguous().to(dev), test_mode=True).cpu()
+    ferr = max_abs(feat[0].cpu(), a["feature0"])
+    err = max_abs(out, a["out"])
+    print(f"config 2 ({engine}): feature max-abs {ferr:.2e} (std {meta['feature_std']:.2f}), output max-abs {err:.2e}")
+    assert ferr < 5e-5, ferr
+    assert err < TOL, err
+
+
+def test_config2_psnr_y_parity():
+    """PSNR-Y of our frame and of the reference's frame against the same synthetic ground truth, through
+    metrics.psnr (uint8 rounding, crop_border = scale, Y channel: metrics.py:181-226) must agree to 1e-3 dB
+    (BASELINE.json north_star), and the two frames themselves must be > 80 dB apart."""
+    from ciaosr_b200 import metrics
+    dev = _dev()
+    meta, a = load_case("full_cfg2")
+    bench, m = _bench_model(dev)
+    lq_raw, coord, cell = bench.make_inputs(16, meta["seed"])
+    mean = torch.tensor(bench.RGB_MEAN).view(1, 1, 3)
+    s, n = bench.SCALE, bench.H * bench.SCALE
+    for i in range(2):
+        res = m(lq=lq_raw[i:i + 1].to(dev), gt=None, test_mode=True, coord=coord[i:i + 1].to(dev),
+                cell=cell[i:i + 1].to(dev))["output"]                                # [1,3,192,192] in [0,1]
+        ref = (a["out"][i:i + 1] + mean).clamp(0, 1).view(1, n, n, 3).permute(0, 3, 1, 2)
+        gt = torch.nn.functional.interpolate(lq_raw[i:i + 1], scale_factor=s, mode="bicubic").clamp(0, 1)
+        ours_img, ref_img, gt_img = metrics.tensor2img(res), metrics.tensor2img(ref), metrics.tensor2img(gt)
+        p_ours = metrics.psnr(ours_img, gt_img, s, convert_to="y")
+        p_ref = metrics.psnr(ref_img, gt_img, s, convert_to="y")
+        p_between = metrics.psnr(ours_img, ref_img, s, convert_to="y")
+        print(f"crop {i}: PSNR-Y ours {p_ours:.5f} dB, reference {p_ref:.5f} dB, ours vs reference {p_between:.1f} dB")
+        assert abs(p_ours - p_ref) <= 1e-3
+        assert p_between > 80.0
+
+
+@pytest.mark.parametrize("name", ["full_csattn_c64", "full_csattn_c180"])
+def test_cross_scale_attention_full_tile_golden(name):
+    """CrossScaleAttention on a whole 192x192 tile at C = 64 (L = 9216 keys: the long-K P.V accumulation) and on
+    96x96 at C = 180, against the reference's module run on the CPU (a strided subset of the output is stored)."""
+    from ciaosr_b200.cross_scale_attention import CrossScaleAttention
+    dev = _dev()
+    meta, a = load_case(name)
+    holder = torch.nn.Module()
+    holder.cs_attn = CrossScaleAttention(channel=meta["c"], scale=[2])
+    synth.fill_module(holder, meta["seed"])
+    holder = holder.to(dev)
+    feat = synth.synth_feature(1, meta["c"], meta["n"], meta["n"], meta["seed"]).to(dev)
+    out = holder.cs_attn(feat)
+    st = meta["stride"]
+    err = max_abs(out[:, :, ::st, ::st].cpu(), a["out_sub"])
+    print(f"{name}: max-abs {err:.2e} (output std {meta['out_std']:.2f})")
+    assert err < TOL, err
+
+
+def test_config3_tile_x3_golden():
+    """One BASELINE.json config-3 tile: RDN 16x8 on a 192x192 LR tile -> x3 (331 776 queries, cross-scale attention
+    over 9216 keys) against the reference's forward; every 7th query is stored."""
+    dev = _dev()
+    meta, a = load_case("full_cfg3_x3")
+    bench, m = _bench_model(dev)
+    n, s = meta["n"], meta["scale"]
+    lq = synth.synth_lr_image(1, n, n, meta["seed"]).to(dev)
+    coord = make_coord((n * s, n * s)).unsqueeze(0).to(dev)
+    cell = make_cell((n * s, n * s), coord.shape[1]).unsqueeze(0).to(dev)
+    with torch.no_grad():
+        out = m.generator(lq, coord, cell, test_mode=True)
+    err = max_abs(out[:, ::meta["every"]].cpu(), a["out_sub"])
+    print(f"config 3 tile x3: max-abs {err:.2e}")
+    assert err < TOL, err
+
+
+def test_fractional_scales_tcgen05_golden():
+    """x2.5 / x1.7 with the real head dimensions, so that the tcgen05 engine (not only the fp32 one) is pinned to the
+    reference on non-integer scales."""
+    dev = _dev()
+    meta, a = load_case("full_frac")
+    feat = synth.synth_feature(meta["b"], 64, meta["h"], meta["w"], meta["seed"]).to(dev)
+    x_lr = synth.synth_lr_image(meta["b"], meta["h"], meta["w"], meta["seed"]).to(dev)
+    for engine in _engines(meta):
+        g = build_generator(meta, dev, engine=engine)
+        g.gen_feature = lambda _x, _f=feat: [_f]
+        for tag in meta["tags"]:
+            out = g(x_lr, a[f"coord_{tag}"].to(dev), a[f"cell_{tag}"].to(dev), test_mode=True).cpu()
+            assert max_abs(out, a[f"out_{tag}"]) < TOL, (engine, tag)
+    assert "tcgen05" in _engines(meta)
+
+
+def test_graph_replay_after_larger_shape_and_weight_update():
+    """(1) replaying the CUDA graph of shape A after a larger shape B forced the plan workspaces to grow
+    must still address live memory (graph entries keep their buffers alive); (2) an in-place update of ENCODER
+    weights must not replay a graph that holds the stale packed encoder plan; (3) deepcopy after a forward works."""
+    import copy
+    dev = _dev()
+    bench, m = _bench_model(dev)
+    g = m.generator
+    g.cuda_graph = True
+
+    def inputs(b, n, s, seed):
+        lq = synth.synth_lr_image(b, n, n, seed).to(dev)
+        coord = make_coord((n * s, n * s)).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        cell = make_cell((n * s, n * s), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        return lq, coord, cell
+
+    a_in, b_in = inputs(1, 24, 2, 1), inputs(2, 40, 3, 2)
+    with torch.no_grad():
+        a0 = g(*a_in, test_mode=True).clone()
+        g(*b_in, test_mode=True)                       # larger: workspaces are re-allocated
+        junk = [torch.full((1 << 22,), float("nan"), device=dev) for _ in range(8)]     # recycle any freed block
+        a1 = g(*a_in, test_mode=True)
+        del junk
+        assert torch.equal(a0, a1)
+        g.cuda_graph = False
+        assert max_abs(g(*a_in, test_mode=True), a0) == 0.0
+        g.cuda_graph = True
+        # (2) encoder weight update in place
+        g.sfe2.weight.mul_(1.01)
+        a2 = g(*a_in, test_mode=True)
+        g.cuda_graph = False
+        a2_eager = g(*a_in, test_mode=True)
+        assert max_abs(a2, a2_eager) == 0.0
+        assert max_abs(a2, a0) > 0.0
+    # (3)
+    g2 = copy.deepcopy(g)
+    with torch.no_grad():
+        assert max_abs(g2(*a_in, test_mode=True), a2_eager) == 0.0

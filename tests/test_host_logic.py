@@ -126,3 +126,24 @@ def test_reference_edsr_config_is_broken_upstream():
     name = "001_localimplicitsr_edsr_div2k_g1_c64b16_1000k_unfold_lec_mulwkv_res_nonlocal.py"
     with pytest.raises(SyntaxError):
         compile(open(os.path.join(REF_CONFIGS, name)).read(), name, "exec")
+
+
+def test_native_state_lives_outside_the_module():
+    """plans / graphs hold ctypes structs with pointers; they are cached outside the nn.Module so that
+    copy.deepcopy and pickle of a generator that has already run keep working, and a copy starts with no cache."""
+    import copy
+    import ctypes
+    import pickle
+    from ciaosr_b200 import _lib, native
+    from tests.util import build_generator
+    g = build_generator(dict(c=8, hidden=[16], eval_bsize=None, local_size=2, non_local=True, seed=1))
+    desc = _lib.HeadDesc()                                       # what a live HeadPlan carries
+    desc.imnet_q.weight[0] = ctypes.addressof(ctypes.c_float(1.0))
+    native.module_cache(g)["plan"] = desc
+    native.module_cache(g.imnet_q.layers[0])["linear_plan"] = ("key", desc)
+    assert g._plan is desc
+    g2 = copy.deepcopy(g)
+    assert g2._plan is None and not native.module_cache(g2.imnet_q.layers[0])
+    g3 = pickle.loads(pickle.dumps(g))
+    assert g3._plan is None
+    assert all(torch.equal(a, b) for a, b in zip(g.state_dict().values(), g2.state_dict().values()))

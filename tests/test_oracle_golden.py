@@ -72,3 +72,29 @@ def test_flop_model():
     assert orc.head_flops_per_query(64) == 8865280
     assert orc.head_flops_per_query(180) == 18486784
     assert orc.head_flops_per_query(180, non_local=False) == 17657344
+
+
+# ---- BASELINE-size goldens (oracle/make_golden_full.py) --------------------------------------------------------
+def test_head_full_frac():
+    """Fractional scales at the real head dimensions (C = 64, hidden 256x4)."""
+    meta, a = load_case("full_frac")
+    from ciaosr_b200 import synth
+    w = head_weights(build_generator(meta))
+    feat = synth.synth_feature(meta["b"], 64, meta["h"], meta["w"], meta["seed"])
+    x_lr = synth.synth_lr_image(meta["b"], meta["h"], meta["w"], meta["seed"])
+    for tag in meta["tags"]:
+        out = orc.head_forward(x_lr, feat, a[f"coord_{tag}"], a[f"cell_{tag}"], w, eval_bsize=meta["eval_bsize"])
+        assert max_abs(out, a[f"out_{tag}"]) < TOL, tag
+
+
+def test_head_config2_crop():
+    """BASELINE.json config 2, one crop: the oracle head on the reference encoder's own feature map (stored with
+    the golden) against the reference's end-to-end output: pins the oracle at the size bench.py times."""
+    import bench
+    meta, a = load_case("full_cfg2")
+    m = bench.build_model()
+    w = {k: v.detach() for k, v in m.generator.state_dict().items()}
+    lq, coord, cell = bench.make_inputs(16, meta["seed"])
+    lq = lq - torch.tensor(bench.RGB_MEAN).view(1, 3, 1, 1)
+    out = orc.head_forward(lq[:1], a["feature0"][None], coord[:1], cell[:1], w, eval_bsize=bench.EVAL_BSIZE)
+    assert max_abs(out, a["out"][:1]) < TOL

@@ -102,6 +102,62 @@ def calibrate_features(gen, dev, target_std=0.5):
         return float(gen.gen_feature(x)[0].std())
 
 
+def prepare(case, dev, cuda_graph=True):
+    """Build one case's restorer with synthetic weights on `dev`: (model, test generator, raw LR frame, coord/cell
+    kwargs for un-tiled cases, test_cfg, synthetic feature std for the calibrated SwinIR trunks)."""
+    from ciaosr_b200 import synth
+    from ciaosr_b200.builder import build
+    from ciaosr_b200.coords import make_cell, make_coord
+    cfg, test_cfg = case["build"]()
+    m = build(cfg, test_cfg=test_cfg)
+    synth.fill_module(m.generator, 0)
+    if getattr(m, "generator_ema", None) is not None:
+        m.generator_ema.load_state_dict(m.generator.state_dict())
+    m = m.eval().to(dev)
+    gen = m._test_generator()
+    feat_std = calibrate_features(gen, dev) if case["config"] in (4, 5) else None
+    gen.cuda_graph = cuda_graph
+    h, w, s = case["h"], case["w"], case["scale"]
+    lq = (synth.synth_lr_image(1, h, w, 7) + torch.tensor(RGB_MEAN).view(1, 3, 1, 1)).to(dev)
+    kw = {}
+    if not test_cfg.get("tile"):
+        kw = dict(coord=make_coord((h * s, w * s)).unsqueeze(0).to(dev),
+                  cell=make_cell((h * s, w * s), h * s * w * s).unsqueeze(0).to(dev))
+    return m, gen, lq, kw, test_cfg, feat_std
+
+
+def run_frame(model, x, kw, world=1):
+    """forward_test minus its final .cpu(): the blended, de-normalised, clamped frame [1, Ho*Wo, 3] on the device.
+    With a process group, tiles (tiled cases) or bands of the coordinate list (un-tiled) are sharded over the ranks
+    and assembled by one all-gather (ciaosr_b200/dist.py)."""
+    x = (x - model.lq_mean.to(x)) / model.lq_std.to(x)
+    model.gt_mean, model.gt_std = model.gt_mean.to(x), model.gt_std.to(x)
+    g = model._test_generator()
+    with torch.no_grad():
+        if model.test_cfg.get("tile"):
+            return model.clip_test(x, g, denorm=True)
+        if world > 1:
+            from ciaosr_b200 import dist as cdist
+            p = cdist.sharded_query_forward(g, x, kw["coord"], kw["cell"], g.eval_bsize)
+        else:
+            p = g(x, kw["coord"], kw["cell"], test_mode=True)
+        return (p * model.gt_std + model.gt_mean).clamp_(0, 1)
+
+
+def run_alone(model, x, kw):
+    """The same frame computed by this rank alone (no sharding): the reference for the bit-equality check."""
+    gen = model._test_generator()
+    x = (x - model.lq_mean.to(x)) / model.lq_std.to(x)
+    with torch.no_grad():
+        if model.test_cfg.get("tile"):
+            model.test_cfg["shard_tiles"] = False
+            try:
+                return model.clip_test(x, gen, denorm=True)
+            finally:
+                model.test_cfg["shard_tiles"] = True
+        return (gen(x, kw["coord"], kw["cell"], test_mode=True) * model.gt_std + model.gt_mean).clamp_(0, 1)
+
+
 def psnr(a, b):
     mse = float(((a.double() - b.double()) ** 2).mean())
     return 200.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)
@@ -133,36 +189,11 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     lines = []
     for case in cases({int(c) for c in args.configs.split(",")}):
-        cfg, test_cfg = case["build"]()
-        m = build(cfg, test_cfg=test_cfg)
-        synth.fill_module(m.generator, 0)
-        if getattr(m, "generator_ema", None) is not None:
-            m.generator_ema.load_state_dict(m.generator.state_dict())
-        m = m.eval().to(dev)
-        gen = m._test_generator()
-        feat_std = calibrate_features(gen, dev) if case["config"] in (4, 5) else None
-        gen.cuda_graph = True
+        m, gen, lq, kw, test_cfg, feat_std = prepare(case, dev)
         h, w, s = case["h"], case["w"], case["scale"]
-        lq = (synth.synth_lr_image(1, h, w, 7) + torch.tensor(RGB_MEAN).view(1, 3, 1, 1)).to(dev)
-        kw = {}
-        if not test_cfg.get("tile"):
-            kw = dict(coord=make_coord((h * s, w * s)).unsqueeze(0).to(dev),
-                      cell=make_cell((h * s, w * s), h * s * w * s).unsqueeze(0).to(dev))
 
         def run(model=m, x=lq, kw=kw):
-            # forward_test minus its final .cpu(): the blended, de-normalised, clamped frame on the device
-            x = (x - model.lq_mean.to(x)) / model.lq_std.to(x)
-            model.gt_mean, model.gt_std = model.gt_mean.to(x), model.gt_std.to(x)
-            g = model._test_generator()
-            with torch.no_grad():
-                if model.test_cfg.get("tile"):
-                    return model.clip_test(x, g, denorm=True)
-                if world > 1:       # bands of the coordinate list per rank, one all-gather (ciaosr_b200/dist.py)
-                    from ciaosr_b200 import dist as cdist
-                    p = cdist.sharded_query_forward(g, x, kw["coord"], kw["cell"], g.eval_bsize)
-                else:
-                    p = g(x, kw["coord"], kw["cell"], test_mode=True)
-                return (p * model.gt_std + model.gt_mean).clamp_(0, 1)
+            return run_frame(model, x, kw, world)
 
         torch.cuda.reset_peak_memory_stats(dev)
         out = run()
@@ -193,15 +224,7 @@ def main():
                            if test_cfg.get("tile") else 1))
         if world > 1 and args.check:
             # the sharded frame must equal the frame this rank computes alone (no collective inside)
-            x = (lq - m.lq_mean.to(lq)) / m.lq_std.to(lq)
-            with torch.no_grad():
-                if test_cfg.get("tile"):
-                    m.test_cfg["shard_tiles"] = False
-                    alone = m.clip_test(x, gen, denorm=True)
-                    m.test_cfg["shard_tiles"] = True
-                else:
-                    alone = (gen(x, kw["coord"], kw["cell"], test_mode=True) * m.gt_std + m.gt_mean).clamp_(0, 1)
-            line["check_sharded_vs_single_max_abs"] = float((alone - out).abs().max())
+            line["check_sharded_vs_single_max_abs"] = float((run_alone(m, lq, kw) - out).abs().max())
         if args.stages and world == 1:
             # one eager pass with the library's per-stage CUDA events; "encoder+glue" is the remainder
             from ciaosr_b200 import native
