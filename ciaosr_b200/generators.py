@@ -121,14 +121,38 @@ class LocalImplicitSRNet(nn.Module):
     # -- reference API -----------------------------------------------------------------
     def forward(self, x, coord, cell, test_mode=False):
         """x [B,3,H,W] normalised LR, coord/cell [B,Q,2] (y,x) -> [B,Q,3]."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not test_mode:
-            raise NotImplementedError(
-                "ciaosr_b200 implements the inference forward of the head only; run training "
-                "forwards under torch.no_grad() or with test_mode=True (SURVEY.md 8f #4)")
+        if torch.is_grad_enabled() and not test_mode and (x.requires_grad or any(
+                p.requires_grad for p in self.parameters())):
+            return self._forward_train(x, coord, cell)
         with torch.no_grad():
             if self.cuda_graph and x.is_cuda:
                 return self._forward_graphed(x, coord, cell, test_mode)
             return self._forward_eager(x, coord, cell, test_mode)
+
+    def _forward_train(self, x, coord, cell):
+        """Training forward (ciaosr.py:88 -> ciaosr_net.py:98-108 with test_mode=False: no eval_bsize chunking): the
+        encoder runs in PyTorch under autograd, the head's VALUE comes from the native kernels and its gradient from
+        a recompute with differentiable torch ops (head_autograd.HeadFunction; SURVEY.md 8f #4)."""
+        from .head_autograd import HeadFunction
+        if not x.is_cuda:
+            raise RuntimeError("ciaosr_b200 has no CPU path for the head (training forward included)")
+        feature = self.gen_feature(x)
+        if len(feature) != 1:
+            raise NotImplementedError("every reference encoder returns exactly one feature map")
+        params = self._head_params_live()
+        hyper = dict(engine=self.engine, local_size=self.local_size, non_local_attn=self.non_local_attn,
+                     softmax_scale=float(self.softmax_scale),
+                     cs_softmax_scale=float(self.cs_attn.softmax_scale) if self.non_local_attn else 10.0)
+        return HeadFunction.apply(self.head_plan(), hyper, feature[0].contiguous(), coord.contiguous(),
+                                  cell.contiguous(), x.detach().contiguous() if self.res else None,
+                                  tuple(params), *params.values())
+
+    def _head_params_live(self):
+        """The head's parameters / buffers themselves (not detached copies), keyed like the state_dict."""
+        prefixes = ("imnet_q.", "imnet_k.", "imnet_v.", "cs_attn.")
+        live = dict(self.named_parameters())
+        live.update(dict(self.named_buffers()))
+        return {k: v for k, v in live.items() if k.startswith(prefixes)}
 
     def _forward_eager(self, x, coord, cell, test_mode):
         xin = x.contiguous(memory_format=torch.channels_last) if (self.channels_last and x.is_cuda) else x

@@ -56,7 +56,35 @@ class BasicRestorer(nn.Module):
     def forward(self, lq, gt=None, test_mode=False, **kwargs):
         if test_mode:
             return self.forward_test(lq, gt, **kwargs)
-        raise NotImplementedError("training forward is out of scope for ciaosr_b200 (SURVEY.md 8f #4)")
+        return self.forward_train(lq, gt, **kwargs)
+
+    def forward_train(self, lq, gt, **kwargs):
+        """basic_restorer.py:84-99 (the implicit generators also need coord / cell)."""
+        output = self.generator(lq, **kwargs)
+        return dict(losses=dict(loss_pix=self.pixel_loss(output, gt)), num_samples=len(gt.data),
+                    results=dict(lq=lq.cpu(), gt=gt.cpu(), output=output.detach().cpu()))
+
+    @staticmethod
+    def parse_losses(losses):
+        """mmedit BaseModel.parse_losses: sum every entry whose key contains 'loss'; log_vars as Python floats
+        (averaged over the process group when one is initialised)."""
+        import torch.distributed as tdist
+        log_vars = {}
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            elif isinstance(value, list):
+                log_vars[name] = sum(v.mean() for v in value)
+            else:
+                raise TypeError(f"{name} is not a tensor or list of tensors")
+        loss = sum(v for k, v in log_vars.items() if "loss" in k)
+        log_vars["loss"] = loss
+        for name in log_vars:
+            v = log_vars[name].detach().clone()
+            if tdist.is_available() and tdist.is_initialized():
+                tdist.all_reduce(v.div_(tdist.get_world_size()))
+            log_vars[name] = v.item()
+        return loss, log_vars
 
     def evaluate(self, output, gt):
         """basic_restorer.py:101-124: metrics on uint8 images with crop_border / convert_to."""
@@ -79,6 +107,22 @@ class CiaoSR(BasicRestorer):
         rgb_mean, rgb_std = torch.FloatTensor(rgb_mean), torch.FloatTensor(rgb_std)
         self.lq_mean, self.lq_std = rgb_mean.view(1, -1, 1, 1), rgb_std.view(1, -1, 1, 1)
         self.gt_mean, self.gt_std = rgb_mean.view(1, 1, -1), rgb_std.view(1, 1, -1)
+
+    def train_step(self, data_batch, optimizer):
+        """ciaosr.py:60-109: normalise, generator(lq, coord, cell), pixel loss, one optimizer step."""
+        coord, cell, lq, gt = data_batch["coord"], data_batch["cell"], data_batch["lq"], data_batch["gt"]
+        self.lq_mean, self.lq_std = self.lq_mean.to(lq), self.lq_std.to(lq)
+        self.gt_mean, self.gt_std = self.gt_mean.to(gt), self.gt_std.to(gt)
+        lq = (lq - self.lq_mean) / self.lq_std
+        gt = (gt - self.gt_mean) / self.gt_std
+        pred = self.generator(lq, coord, cell)
+        loss, log_vars = self.parse_losses(dict(loss_pix=self.pixel_loss(pred, gt)))
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        log_vars.pop("loss")
+        return dict(log_vars=log_vars, num_samples=len(gt.data),
+                    results=dict(lq=lq.cpu(), gt=gt.cpu(), output=pred.detach().cpu()))
 
     def forward_test(self, lq, gt=None, coord=None, cell=None, meta=None, save_image=False,
                      save_path=None, iteration=None):

@@ -143,6 +143,32 @@ def swinir_case(name, shapes, seed=0, **kw):
     save(name, dict(kind="swinir", seed=seed, tags=tags, cfg=kw, state_keys=keys), arrays)
 
 
+def train_case(name, c, hidden, b, h, w, nq, local_size=2, seed=0):
+    """Gradients of the training forward (ciaosr.py:88-95: generator(lq, coord, cell) with test_mode=False -> L1
+    loss) with respect to the feature map and every head parameter, from the reference's own autograd graph."""
+    g = rh.build_reference_generator("edsr", c, hidden, num_blocks=1, eval_bsize=None, local_size=local_size)
+    synth.fill_module(g, seed)
+    g.train()
+    feature = synth.synth_feature(b, c, h, w, seed).requires_grad_(True)
+    x_lr = synth.synth_lr_image(b, h, w, seed)
+    g.gen_feature = lambda _x: [feature]
+    rs = np.random.RandomState(seed + 23)
+    coord = torch.from_numpy(rs.uniform(-1, 1, size=(b, nq, 2)).astype(np.float32))
+    sc = rs.uniform(1.0, 4.0, size=(b, 1, 1)).astype(np.float32)
+    cell = torch.from_numpy(np.broadcast_to(np.concatenate([2.0 / (h * sc), 2.0 / (w * sc)], axis=2), (b, nq, 2)).copy())
+    gt = torch.from_numpy(rs.uniform(-0.5, 0.5, size=(b, nq, 3)).astype(np.float32))
+    pred = g(x_lr, coord, cell)
+    loss = (pred - gt).abs().mean()
+    loss.backward()
+    arrays = dict(coord=coord.numpy(), cell=cell.numpy(), gt=gt.numpy(), pred=pred.detach().numpy(),
+                  loss=np.array([float(loss)], dtype=np.float32), grad_feature=feature.grad.numpy())
+    for k, v in g.named_parameters():
+        if k.startswith(("imnet_", "cs_attn.")) and v.grad is not None:
+            arrays["grad__" + k] = v.grad.numpy()
+    save(name, dict(kind="train", c=c, hidden=list(hidden), b=b, h=h, w=w, nq=nq, local_size=local_size, seed=seed,
+                    non_local=True, eval_bsize=None), arrays)
+
+
 def save(name, meta, arrays):
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
@@ -151,9 +177,12 @@ def save(name, meta, arrays):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB  {meta}")
 
 
-def main():
+def main(only=()):
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if only:                                  # python -m oracle.make_golden train_small : just the named late additions
+        train_case("train_small", 16, (32, 32), 2, 7, 6, 60, seed=16)
+        return
     # generic small shapes (SIMT engine): odd H (reflect pad), non-square, several chunks
     head_case("head_small", 8, (32, 32), 2, 7, 6, [2, 3], eval_bsize=100, random_q=150)
     head_case("head_frac", 8, (16,), 1, 6, 5, [2.5, 1.7], eval_bsize=None, seed=1)
@@ -176,10 +205,12 @@ def main():
     # tiled inference through the restorer
     clip_case("clip_small", 16, (32, 32), 40, 36, 2, 24, 8, seed=9)
     real_clip_case("clip_real_small", 16, (32, 32), 30, 44, 4, 16, 4, seed=15)
+    # training forward + backward through the reference's autograd graph
+    train_case("train_small", 16, (32, 32), 2, 7, 6, 60, seed=16)
     # SwinIR trunk: window-multiple size (buffered shift mask), padded sizes (reflect pad + recomputed mask)
     swinir_case("swinir_trunk", [(1, 8, 8), (2, 10, 13), (1, 16, 12)], seed=10,
                 embed_dim=24, depths=(2, 2), num_heads=(2, 2), window_size=4, img_size=8, mlp_ratio=2)
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))

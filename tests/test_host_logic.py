@@ -67,10 +67,12 @@ def test_no_cpu_path():
         g(x, coord, torch.ones_like(coord), test_mode=True)
 
 
-def test_training_forward_is_refused():
+def test_training_forward_has_no_cpu_path_either():
+    """The training forward takes its value from the native kernels too (head_autograd.HeadFunction); on CPU
+    tensors it refuses like the inference forward."""
     g = build(generator_cfg(8, (8,))).train()
     coord = make_coord((4, 4)).unsqueeze(0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         g(torch.zeros(1, 3, 4, 4), coord, torch.ones_like(coord))
 
 
