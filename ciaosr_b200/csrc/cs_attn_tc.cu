@@ -1,12 +1,25 @@
 // Cross-scale non-local attention on the tensor cores (arch_csnln.py:430-532).
 //
-// Same attention form as cs_attn.cu (see its header), with the three large contractions on
-// tcgen05 through the generic functor GEMM (gemm_tc.cuh, fp16 hi/lo split x3 = fp32-grade):
-//   S = 10 * Q K^T        A = 3x3 patches of Mi (implicit), B = normalised 3x3 patches of R (packed per image)
-//   O = P V               A = softmax rows,                 B = V^T: 6x6 stride-2 patches of E (packed per image)
-//   out = down(canvas)/6  A = 3x3 stride-2 patches of the folded canvas, B = down-conv weights
-// The 1x1 embeddings, the row softmax and the fold stay on CUDA cores (they are bandwidth-trivial),
-// batched over all images of the call.
+// Same attention form as cs_attn.cu (see its header), with the two large contractions on tcgen05 through the
+// generic functor GEMM (gemm_tc.cuh, fp16 hi/lo split x3 = fp32-grade):
+//   S = 10 * Q K^T        A = 3x3 patches of Mi (TMA-loaded),  B = normalised 3x3 patches of R (packed per image)
+//   T = P V'              A = softmax rows (TMA-loaded),       B = the SHIFTED, down-convolved value patches V'
+//
+// "Shifted values" (round 2).  The reference's tail is  out = conv3x3_s2(fold(P V)) / 6  with V = 6x6 stride-2
+// patches of E (36 C columns), a [HW, 36C] intermediate O, an overlap-add and a strided convolution.  All three
+// are linear, so the convolution is pushed through the fold onto the values: output pixel (Y, X) only receives from
+// query pixels (Y + dy, X + dx), dy, dx in {-2, -1, 0, +1}, and
+//   out[(Y,X), co] = ( sum_{dy,dx} sum_l P[(Y+dy, X+dx), l] * V'_{dy,dx}[l, co] + b[co] ) / 6
+//   V'_{dy,dx}[l, co] = sum_{u in U(dy), v in U(dx)} G[(ly - dy, lx - dx), u, v, co]
+//   G[(y', x'), u, v, co] = sum_ci Wdown[co, ci, u, v] * E_zero-padded[ci, 2y' - 1 + u, 2x' - 1 + v]
+//   U(-2) = {0}, U(-1) = U(0) = {0, 1, 2}, U(+1) = {1, 2}      (patch row i = 1 + u - 2 dy must lie in [0, 6))
+// so the long-K GEMM has 16 C columns instead of 36 C (2.25x fewer FLOPs), its output T = P V' [HW, 16 C] is
+// reduced by a 16-term gather, and O / the canvas / the down GEMM are gone.  One boundary effect: conv_transpose2d
+// crops canvas row / column -1, which the u = 0 (v = 0) taps of output row Y = 0 (column X = 0) would read; those
+// terms are removed by a second, tiny GEMM over the Hp + Wp boundary query rows (inclusion-exclusion at the corner).
+// Verified against the oracle to 4e-7 (tests; prototype in the round-2 notes of DESIGN.md).
+// The 1x1 embeddings, G, the row softmax and the final gather stay on CUDA cores (bandwidth-trivial), batched over
+// all images of the call.
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -137,30 +150,116 @@ static int softmax_rows_split(const float* s, split_t* p_hi, split_t* p_lo, long
   return CIAOSR_OK;
 }
 
-__global__ void csa_fold_batch_kernel(const float* __restrict__ o, float* __restrict__ cv, int Hp, int Wp,
-                                      int C, long long total) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  const long long p = i / C;
-  const int W2 = 2 * Wp, H2 = 2 * Hp;
-  const int X = (int)(p % W2), Y = (int)((p / W2) % H2);
-  const long long img = p / ((long long)W2 * H2);
-  const float* oi = o + img * Hp * Wp * 36LL * C;
-  float acc = 0.0f;
+// ---- shifted values ---------------------------------------------------------------------------------------------
+// G on the key grid extended by 2 on every side (shifted keys ly - dy fall outside [0, Hl) at the borders; E is
+// zero there, which is exactly the zero padding of the value patches), stored as planes [img][uv][co][He][We] so
+// that the operand packers read consecutive keys from consecutive addresses.
+constexpr int CSA_GKEYS = 4;               // extended keys per block (reuse of the down-conv weights)
+__global__ void __launch_bounds__(256) csa_gtap_kernel(const float* __restrict__ e, const float* __restrict__ wdt,
+                                                       float* __restrict__ g, int Hp, int Wp, int He, int We, int C) {
+  extern __shared__ float es[];            // [CSA_GKEYS][9][C]
+  const int img = blockIdx.y;
+  const int key0 = blockIdx.x * CSA_GKEYS, nkeys = He * We;
+  for (int i = threadIdx.x; i < CSA_GKEYS * 9 * C; i += blockDim.x) {
+    const int kk = i / (9 * C), r = i - kk * 9 * C, uv = r / C, ci = r - uv * C;
+    const int key = key0 + kk;
+    float v = 0.0f;
+    if (key < nkeys) {
+      const int y = 2 * (key / We - 2) - 1 + uv / 3, x = 2 * (key % We - 2) - 1 + uv % 3;
+      if (y >= 0 && y < Hp && x >= 0 && x < Wp) v = e[(((long long)img * Hp + y) * Wp + x) * C + ci];
+    }
+    es[i] = v;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 9 * C; o += blockDim.x) {
+    const int uv = o / C, co = o - uv * C;
+    const float* wcol = wdt + (long long)uv * C * C + co;          // Wdown^T[(uv*C + ci), co]
+    float acc[CSA_GKEYS] = {};
+    for (int ci = 0; ci < C; ++ci) {
+      const float wv = __ldg(wcol + (long long)ci * C);
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const int y = Y / 2 + 1 - a;
+      for (int kk = 0; kk < CSA_GKEYS; ++kk) acc[kk] = fmaf(es[(kk * 9 + uv) * C + ci], wv, acc[kk]);
+    }
+    float* dst = g + (((long long)img * 9 + uv) * C + co) * nkeys + key0;
+#pragma unroll
+    for (int kk = 0; kk < CSA_GKEYS; ++kk)
+      if (key0 + kk < nkeys) dst[kk] = acc[kk];
+  }
+}
+
+// rows of the boundary query pixels, copied out of the split P matrices: per image rows [0, Wp) = queries (0, x),
+// rows [Wp, Wp + Hp) = queries (y, 0), zero up to rows_b (a multiple of 128, so GEMM tiles do not straddle images)
+__global__ void csa_boundary_rows_kernel(const split_t* __restrict__ p_hi, const split_t* __restrict__ p_lo,
+                                         split_t* __restrict__ b_hi, split_t* __restrict__ b_lo, int Hp, int Wp,
+                                         int rows_b, int ldp) {
+  const int r = blockIdx.x, img = blockIdx.y;
+  long long src = -1;
+  if (r < Wp) src = (long long)img * Hp * Wp + r;
+  else if (r < Wp + Hp) src = (long long)img * Hp * Wp + (long long)(r - Wp) * Wp;
+  const long long dst = ((long long)img * rows_b + r) * ldp;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < ldp / 8; i += blockDim.x) {
+    reinterpret_cast<uint4*>(b_hi + dst)[i] = src >= 0 ? reinterpret_cast<const uint4*>(p_hi + src * ldp)[i] : z;
+    reinterpret_cast<uint4*>(b_lo + dst)[i] = src >= 0 ? reinterpret_cast<const uint4*>(p_lo + src * ldp)[i] : z;
+  }
+}
+
+// out[(Y,X), co] = (sum of the 16 shifted T rows - boundary corrections + b) / 6, cropped to H x W
+__global__ void csa_shift_gather_kernel(const float* __restrict__ t, const float* __restrict__ tb,
+                                        const float* __restrict__ bias, float* __restrict__ o_nhwc, int ldo,
+                                        float* __restrict__ o_nchw, int H, int W, int Hp, int Wp, int C, int rows_b,
+                                        long long img0, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // one thread per 4 output channels
+  if (i >= total) return;
+  const int c4 = C / 4;
+  const int co = (int)(i % c4) * 4;
+  const long long p = i / c4;
+  const int X = (int)(p % W), Y = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  const int nv = 16 * C, nc = 9 * C;
+  const float* ti = t + img * Hp * Wp * (long long)nv;
+  const float* bi = tb + img * rows_b * (long long)nc;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [&](const float* src, float sign) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    acc.x = fmaf(sign, v.x, acc.x); acc.y = fmaf(sign, v.y, acc.y);
+    acc.z = fmaf(sign, v.z, acc.z); acc.w = fmaf(sign, v.w, acc.w);
+  };
+#pragma unroll
+  for (int dyi = 0; dyi < 4; ++dyi) {
+    const int y = Y + dyi - 2;
     if (y < 0 || y >= Hp) continue;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int x = X / 2 + 1 - b;
+    for (int dxi = 0; dxi < 4; ++dxi) {
+      const int x = X + dxi - 2;
       if (x < 0 || x >= Wp) continue;
-      const int ij = (Y % 2 + 2 * a) * 6 + (X % 2 + 2 * b);
-      acc += oi[((long long)y * Wp + x) * (36LL * C) + (long long)ij * C + c];
+      add(ti + ((long long)y * Wp + x) * nv + (dyi * 4 + dxi) * C + co, 1.0f);
     }
   }
-  cv[i] = acc;
+  if (Y == 0) {
+#pragma unroll
+    for (int dxi = 0; dxi < 4; ++dxi) {
+      const int x = X + dxi - 2;
+      if (x >= 0 && x < Wp) add(bi + (long long)x * nc + dxi * C + co, -1.0f);
+    }
+  }
+  if (X == 0) {
+#pragma unroll
+    for (int dyi = 0; dyi < 4; ++dyi) {
+      const int y = Y + dyi - 2;
+      if (y >= 0 && y < Hp) add(bi + (long long)(Wp + y) * nc + (4 + dyi) * C + co, -1.0f);
+    }
+  }
+  if (Y == 0 && X == 0) add(bi + 8 * C + co, 1.0f);
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co));
+  const float r0 = __fdiv_rn(acc.x + b4.x, 6.0f), r1 = __fdiv_rn(acc.y + b4.y, 6.0f);
+  const float r2 = __fdiv_rn(acc.z + b4.z, 6.0f), r3 = __fdiv_rn(acc.w + b4.w, 6.0f);
+  const long long hw = (long long)Y * W + X, gm = (img0 + img) * H * W + hw;
+  if (o_nhwc) *reinterpret_cast<float4*>(o_nhwc + gm * ldo + co) = make_float4(r0, r1, r2, r3);
+  if (o_nchw) {
+    float* dst = o_nchw + ((img0 + img) * C + co) * (long long)H * W + hw;
+    dst[0] = r0; dst[(long long)H * W] = r1; dst[2LL * H * W] = r2; dst[3LL * H * W] = r3;
+  }
 }
 
 // ---- operand sources for the per-image blobs ----------------------------------------------------
@@ -173,18 +272,30 @@ struct KhatSrc {            // B[n = l, k = t*Chp + c] = R_pad[l + tap t, c] / m
     return __fdiv_rn(r[(((long long)img * Hl + y) * Wl + x) * Ch + c], nrm[(long long)img * Hl * Wl + n]);
   }
 };
-struct VtSrc {              // B[n = (i*6+j)*C + c, k = l] = E_pad[c, 2ly-2+i, 2lx-2+j]
-  const float* e; int Hp, Wp, Wl, C, img0;
+// B[n, k = l] of the shifted-value GEMMs, summed from the G planes.  Column n decodes to (dy, dx, row-tap mask,
+// column-tap mask, co):  main blob  n = (dyi*4 + dxi)*C + co with masks U(dy), U(dx);  correction blob (corr = 1)
+// n in [0,4C): dy = 0, u = {0}, dx = n/C - 2 with U(dx);  [4C,8C): dx = 0, v = {0}, dy with U(dy);  [8C,9C): corner.
+struct VShiftSrc {
+  const float* g; int Hl, Wl, He, We, C, img0, corr;
   __device__ __forceinline__ float operator()(int image, int n, int k) const {
-    const int img = img0 + image, ij = n / C, c = n % C;
-    const int y = 2 * (k / Wl) - 2 + ij / 6, x = 2 * (k % Wl) - 2 + ij % 6;
-    if (y < 0 || y >= Hp || x < 0 || x >= Wp) return 0.0f;
-    return e[(((long long)img * Hp + y) * Wp + x) * C + c];
+    const int UM[4] = {1, 7, 7, 6};                 // bit u set <=> tap u contributes, for dy = -2, -1, 0, +1
+    const int blk = n / C, co = n - blk * C;
+    int dy, dx, um, vm;
+    if (!corr) { dy = (blk >> 2) - 2; dx = (blk & 3) - 2; um = UM[blk >> 2]; vm = UM[blk & 3]; }
+    else if (blk < 4) { dy = 0; dx = blk - 2; um = 1; vm = UM[blk]; }
+    else if (blk < 8) { dy = blk - 6; dx = 0; um = UM[blk - 4]; vm = 1; }
+    else { dy = 0; dx = 0; um = 1; vm = 1; }
+    const int ye = k / Wl - dy + 2, xe = k % Wl - dx + 2;            // always inside the extended grid
+    const long long plane = (long long)He * We;
+    const float* src = g + ((long long)(img0 + image) * 9 * C + co) * plane + (long long)ye * We + xe;
+    float acc = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+        if (((um >> u) & 1) && ((vm >> v) & 1)) acc += __ldg(src + (long long)(u * 3 + v) * C * plane);
+    return acc;
   }
-};
-struct DownSrc {            // B[n = co, k = (u*3+v)*C + ci] = down_wt[k, co]
-  const float* w; int C;
-  __device__ __forceinline__ float operator()(int, int n, int k) const { return w[(long long)k * C + n]; }
 };
 
 // ---- A generators / epilogues ----------------------------------------------------------------------
@@ -251,70 +362,24 @@ struct OutEpi {             // O[m, n] = sc * acc, n < N (N % 4 == 0); accumulat
                              fmaf(sc, v[4 * j + 2], old[j].z), fmaf(sc, v[4 * j + 3], old[j].w));
   }
 };
-struct DownGen {            // rows = cropped output pixels (img, y, x); k = (u*3+v)*C + ci
-  const float* cv; int H, W, H2, W2, C, K; long long img0;
-  struct Row { int y, x, hw; long long img; };
-  __device__ __forceinline__ Row row(long long m) const {
-    const int hw = (int)(m % ((long long)H * W));
-    return Row{hw / W, hw % W, hw, m / ((long long)H * W)};
-  }
-  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
-    const float* centre = cv + (((r.img * H2) + 2 * r.y) * W2 + 2 * r.x) * C;    // always inside the canvas
-    const float* src[8];
-    bool ok[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int k = k0 + 4 * g;
-      src[g] = centre; ok[g] = false;
-      if (k < K) {
-        const int uv = k / C, ci = k - uv * C;
-        const int u = uv / 3, w = uv - u * 3;
-        const int Y = 2 * r.y - 1 + u, X = 2 * r.x - 1 + w;
-        ok[g] = Y >= 0 && Y < H2 && X >= 0 && X < W2;
-        if (ok[g]) src[g] = centre + ((u - 1) * W2 + (w - 1)) * C + ci;
-      }
-    }
-    float4 q[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
-      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
-    }
-  }
-};
-struct DownEpi {            // (acc + b) / 6 -> NHWC slice and / or NCHW
-  float* o_nhwc; int ldo; float* o_nchw; int HW, C; const float* bias; long long img0;
-  __device__ __forceinline__ void store(const DownGen::Row& r, long long m, int n0, const float (&v)[32]) const {
-    const long long gm = img0 * HW + m;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int n = n0 + i;
-      if (n < C) {
-        const float val = __fdiv_rn(v[i] + bias[n], 6.0f);
-        if (o_nhwc) o_nhwc[gm * ldo + n] = val;
-        if (o_nchw) o_nchw[((img0 + r.img) * C + n) * HW + r.hw] = val;
-      }
-    }
-  }
-};
-
 // ---- host orchestration ------------------------------------------------------------------------------
 struct CsaTcSizes {
   int Hp, Wp, Hl, Wl, L, ldS, HWp, group;      // group = images processed together
   int Chp, ldP, ldQ;                                // ldP: row stride of the split P matrices (16-bit elements, 16-byte rows)
-  int kq_slabs, kq_units, vt_slabs, vt_units, dn_slabs, dn_units;
+  int He, We, rows_b;                               // extended key grid of G; boundary query rows per image (x128)
+  int kq_slabs, kq_units, vt_slabs, vt_units, vc_units;
 };
 static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   CsaTcSizes s;
   s.Hp = H + (H & 1); s.Wp = W + (W & 1);
   s.Hl = s.Hp / 2; s.Wl = s.Wp / 2; s.L = s.Hl * s.Wl; s.ldS = (s.L + 3) / 4 * 4;
   s.HWp = s.Hp * s.Wp; s.ldP = (s.L + 7) / 8 * 8;
+  s.He = s.Hl + 4; s.We = s.Wl + 4; s.rows_b = (s.Hp + s.Wp + ROWS - 1) / ROWS * ROWS;
   s.Chp = (C / 2 + 3) / 4 * 4;                 // query-embedding channels, zero padded to the float4 gathers
   s.kq_slabs = (9 * s.Chp + KSLAB - 1) / KSLAB; s.ldQ = (9 * s.Chp + 7) / 8 * 8; s.kq_units = (s.L + UNIT_N - 1) / UNIT_N;
-  s.vt_slabs = (s.L + KSLAB - 1) / KSLAB; s.vt_units = (36 * C + UNIT_N - 1) / UNIT_N;
-  s.dn_slabs = (9 * C + KSLAB - 1) / KSLAB; s.dn_units = (C + UNIT_N - 1) / UNIT_N;
+  s.vt_slabs = (s.L + KSLAB - 1) / KSLAB;
+  s.vt_units = (16 * C + UNIT_N - 1) / UNIT_N;      // shifted values: 16 (dy, dx) blocks of C columns
+  s.vc_units = (9 * C + UNIT_N - 1) / UNIT_N;       // boundary corrections: 4 + 4 + 1 blocks
   // images per pass: tiles must not straddle images, and the score tensor stays <= 1 GiB
   long long g = (256LL << 20) / ((long long)s.HWp * s.ldS);
   if (g < 1) g = 1;
@@ -324,9 +389,9 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   return s;
 }
 
-// P.V accumulates 3072 keys per TMEM pass; the passes are summed in fp32 (gemm_tc.cuh).  Measured on a 192x192
-// tile (L = 9216 keys, C = 64; max-abs vs the fp32 engine / time): one pass 5.7e-5 / 8.4 ms, 48 slabs 4.0e-5 /
-// 8.9 ms, 16 slabs 3.1e-5 / 10.6 ms.  CIAOSR_CSA_KCHUNK overrides the slabs per pass (0 = one pass).
+// P.V' accumulates 3072 keys per TMEM pass; the passes are summed in fp32 (gemm_tc.cuh).  Measured in round 1 on a
+// 192x192 tile (L = 9216 keys, C = 64; max-abs vs the fp32 engine): one pass 5.7e-5, 48 slabs 4.0e-5, 16 slabs
+// 3.1e-5 at growing cost.  CIAOSR_CSA_KCHUNK overrides the slabs per pass (0 = one pass).
 static int csa_kchunk() {
   static int kc = -1;
   if (kc < 0) {
@@ -338,7 +403,11 @@ static int csa_kchunk() {
 
 bool cs_attn_tc_ok(const PlanLayout& L) { return L.non_local && L.C % 4 == 0; }
 
-struct CsaTcBufs { float *E, *Mi, *R, *nrm, *S, *O, *cv; split_t *Ph, *Pl, *Qh, *Ql; uint8_t *kblob, *vblob, *dblob; };
+struct CsaTcBufs {
+  float *E, *Mi, *R, *nrm, *G, *S, *T, *Tb;
+  split_t *Ph, *Pl, *Qh, *Ql, *Bh, *Bl;
+  uint8_t *kblob, *vblob, *cblob;
+};
 static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s, int B) {
   CsaTcBufs b;
   const int C = L.C, Ch = C / 2, g = s.group;
@@ -346,16 +415,19 @@ static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s
   b.Mi = a.take<float>((size_t)B * s.HWp * s.Chp);
   b.R = a.take<float>((size_t)B * s.L * Ch);
   b.nrm = a.take<float>((size_t)B * s.L);
+  b.G = a.take<float>((size_t)B * 9 * C * s.He * s.We);
   b.S = a.take<float>((size_t)g * s.HWp * s.ldS);
   b.Qh = a.take<split_t>((size_t)g * s.HWp * s.ldQ);
   b.Ql = a.take<split_t>((size_t)g * s.HWp * s.ldQ);
   b.Ph = a.take<split_t>((size_t)g * s.HWp * s.ldP);
   b.Pl = a.take<split_t>((size_t)g * s.HWp * s.ldP);
-  b.O = a.take<float>((size_t)g * s.HWp * 36 * C);
-  b.cv = a.take<float>((size_t)g * 4 * s.HWp * C);
+  b.Bh = a.take<split_t>((size_t)g * s.rows_b * s.ldP);
+  b.Bl = a.take<split_t>((size_t)g * s.rows_b * s.ldP);
+  b.T = a.take<float>((size_t)g * s.HWp * 16 * C);
+  b.Tb = a.take<float>((size_t)g * s.rows_b * 9 * C);
   b.kblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.kq_slabs, s.kq_units));
   b.vblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.vt_slabs, s.vt_units));
-  b.dblob = a.take<uint8_t>(tc_operand_blob_bytes(s.dn_slabs, s.dn_units));
+  b.cblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.vt_slabs, s.vc_units));
   return b;
 }
 
@@ -387,10 +459,18 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
   if ((rc = gemm_simt(B * s.L, Ch, C, PoolFeatBatchA{featT, H, W, s.Hl, s.Wl, C}, RowMajorB{plan + L.m2_wt, Ch},
                       EpiPrelu{b.R, Ch, plan + L.m2_b, scal + 1}, st))) return rc;
   CIAOSR_LAUNCH(csa_knorm_batch_kernel, B * s.L, 128, 0, st, b.R, b.nrm, s.Hl, s.Wl, Ch, scal);
-  if ((rc = tc_pack_operand(b.dblob, 1, C, 9 * C, 0, DownSrc{plan + L.down_wt, C}, st))) return rc;
+  {
+    // the down convolution applied to E once per (extended key, tap): the building block of the shifted values
+    const int gsm = CSA_GKEYS * 9 * C * (int)sizeof(float);
+    static DynSmemOptIn optin;
+    if (gsm > 48 * 1024 && (rc = optin.ensure(csa_gtap_kernel, gsm))) return rc;
+    dim3 grid(cdiv((long long)s.He * s.We, CSA_GKEYS), B);
+    CIAOSR_LAUNCH(csa_gtap_kernel, grid, 256, gsm, st, b.E, plan + L.down_wt, b.G, s.Hp, s.Wp, s.He, s.We, C);
+  }
 
   const size_t kstride = tc_operand_blob_bytes(s.kq_slabs, s.kq_units);
   const size_t vstride = tc_operand_blob_bytes(s.vt_slabs, s.vt_units);
+  const size_t cstride = tc_operand_blob_bytes(s.vt_slabs, s.vc_units);
   for (int i0 = 0; i0 < B; i0 += s.group) {
     const int g = min(s.group, B - i0);
     const long long rows = (long long)g * s.HWp;
@@ -407,17 +487,24 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
                         ScoreEpi{b.S, s.L, s.ldS, L.cs_softmax_scale}, st, &qmap_hi, &qmap_lo))) return rc;
     }
     if ((rc = softmax_rows_split(b.S, b.Ph, b.Pl, rows, s.L, s.ldS, s.ldP, st))) return rc;
-    CUtensorMap map_hi, map_lo;
+    // T = P V' (16 shifted value blocks), Tb = P[boundary rows] Vcorr
+    VShiftSrc vsrc{b.G, s.Hl, s.Wl, s.He, s.We, C, i0, 0};
+    if ((rc = tc_pack_operand(b.vblob, g, 16 * C, s.L, vstride, vsrc, st))) return rc;
+    vsrc.corr = 1;
+    if ((rc = tc_pack_operand(b.cblob, g, 9 * C, s.L, cstride, vsrc, st))) return rc;
+    CIAOSR_LAUNCH(csa_boundary_rows_kernel, dim3(s.rows_b, g), 128, 0, st, b.Ph, b.Pl, b.Bh, b.Bl, s.Hp, s.Wp,
+                  s.rows_b, s.ldP);
+    CUtensorMap map_hi, map_lo, bmap_hi, bmap_lo;
     if ((rc = tma_make_map_2d(&map_hi, b.Ph, rows, s.ldP)) || (rc = tma_make_map_2d(&map_lo, b.Pl, rows, s.ldP))) return rc;
-    if ((rc = tc_pack_operand(b.vblob, g, 36 * C, s.L, vstride, VtSrc{b.E, s.Hp, s.Wp, s.Wl, C, i0}, st)))
-      return rc;
+    const long long brows = (long long)g * s.rows_b;
+    if ((rc = tma_make_map_2d(&bmap_hi, b.Bh, brows, s.ldP)) || (rc = tma_make_map_2d(&bmap_lo, b.Bl, brows, s.ldP))) return rc;
     if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, csa_kchunk()}, b.vblob,
-                      TmaRowsGen{}, OutEpi{b.O, 36 * C, 1.0f / CSA_P_SCALE}, st, &map_hi, &map_lo))) return rc;
-    const long long ctot = (long long)g * 4 * s.HWp * C;
-    CIAOSR_LAUNCH(csa_fold_batch_kernel, cdiv(ctot, 256), 256, 0, st, b.O, b.cv, s.Hp, s.Wp, C, ctot);
-    if ((rc = tc_gemm(GemmShape{(long long)g * H * W, s.dn_slabs, s.dn_units, (long long)g * H * W, 0}, b.dblob,
-                      DownGen{b.cv, H, W, 2 * s.Hp, 2 * s.Wp, C, 9 * C, 0},
-                      DownEpi{out_nhwc, ldo, out_nchw, H * W, C, plan + L.down_b, i0}, st))) return rc;
+                      TmaRowsGen{}, OutEpi{b.T, 16 * C, 1.0f / CSA_P_SCALE}, st, &map_hi, &map_lo))) return rc;
+    if ((rc = tc_gemm(GemmShape{brows, s.vt_slabs, s.vc_units, s.rows_b, cstride, csa_kchunk()}, b.cblob,
+                      TmaRowsGen{}, OutEpi{b.Tb, 9 * C, 1.0f / CSA_P_SCALE}, st, &bmap_hi, &bmap_lo))) return rc;
+    const long long otot = (long long)g * H * W * (C / 4);
+    CIAOSR_LAUNCH(csa_shift_gather_kernel, cdiv(otot, 256), 256, 0, st, b.T, b.Tb, plan + L.down_b, out_nhwc, ldo,
+                  out_nchw, H, W, s.Hp, s.Wp, C, s.rows_b, (long long)i0, otot);
   }
   return CIAOSR_OK;
 }
