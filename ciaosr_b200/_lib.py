@@ -33,6 +33,8 @@ EXPORTS = (
     "ciaosr_tile_blend_accumulate", "ciaosr_tile_blend_finish",
     "ciaosr_rdn_plan_bytes", "ciaosr_rdn_plan_init", "ciaosr_rdn_workspace_bytes", "ciaosr_rdn_forward",
     "ciaosr_linear_plan_bytes", "ciaosr_linear_plan_init", "ciaosr_linear_forward",
+    "ciaosr_window_attention_forward", "ciaosr_layernorm_forward", "ciaosr_linear_forward_res",
+    "ciaosr_conv3x3_plan_bytes", "ciaosr_conv3x3_plan_init", "ciaosr_conv3x3_nhwc_forward",
 )
 
 
@@ -70,6 +72,11 @@ class RdnDesc(Structure):
 
 class LinearDesc(Structure):
     _fields_ = [("abi_version", c_int32), ("in_features", c_int32), ("out_features", c_int32),
+                ("weight", c_void_p), ("bias", c_void_p)]
+
+
+class Conv3x3Desc(Structure):
+    _fields_ = [("abi_version", c_int32), ("in_channels", c_int32), ("out_channels", c_int32),
                 ("weight", c_void_p), ("bias", c_void_p)]
 
 
@@ -134,6 +141,16 @@ def load():
     lib.ciaosr_linear_plan_init.argtypes = [POINTER(LinearDesc), c_void_p, c_size_t, c_void_p]
     lib.ciaosr_linear_forward.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_longlong, c_int, c_void_p,
                                           c_void_p]
+    lib.ciaosr_window_attention_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                    c_int, c_float, c_void_p, c_void_p]
+    lib.ciaosr_linear_forward_res.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_longlong, c_int, c_void_p,
+                                              c_void_p, c_void_p]
+    lib.ciaosr_conv3x3_plan_bytes.argtypes = [POINTER(Conv3x3Desc), POINTER(c_size_t)]
+    lib.ciaosr_conv3x3_plan_init.argtypes = [POINTER(Conv3x3Desc), c_void_p, c_size_t, c_void_p]
+    lib.ciaosr_conv3x3_nhwc_forward.argtypes = [POINTER(Conv3x3Desc), c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                c_void_p, c_void_p, c_void_p]
+    lib.ciaosr_layernorm_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_longlong, c_int, c_void_p,
+                                             c_void_p]
     for name in EXPORTS[3:]:  # everything after the three non-int getters
         getattr(lib, name).restype = c_int
     if lib.ciaosr_abi_version() != ABI_VERSION:

@@ -205,10 +205,11 @@ __global__ void csa_boundary_rows_kernel(const split_t* __restrict__ p_hi, const
 }
 
 // out[(Y,X), co] = (sum of the 16 shifted T rows - boundary corrections + b) / 6, cropped to H x W
+// tb holds `nparts` partial products of the boundary GEMM (K split), `part_stride` floats apart
 __global__ void csa_shift_gather_kernel(const float* __restrict__ t, const float* __restrict__ tb,
                                         const float* __restrict__ bias, float* __restrict__ o_nhwc, int ldo,
                                         float* __restrict__ o_nchw, int H, int W, int Hp, int Wp, int C, int rows_b,
-                                        long long img0, long long total) {
+                                        int nparts, long long part_stride, long long img0, long long total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // one thread per 4 output channels
   if (i >= total) return;
   const int c4 = C / 4;
@@ -225,6 +226,9 @@ __global__ void csa_shift_gather_kernel(const float* __restrict__ t, const float
     acc.x = fmaf(sign, v.x, acc.x); acc.y = fmaf(sign, v.y, acc.y);
     acc.z = fmaf(sign, v.z, acc.z); acc.w = fmaf(sign, v.w, acc.w);
   };
+  auto add_parts = [&](const float* src, float sign) {
+    for (int p = 0; p < nparts; ++p) add(src + p * part_stride, sign);
+  };
 #pragma unroll
   for (int dyi = 0; dyi < 4; ++dyi) {
     const int y = Y + dyi - 2;
@@ -240,17 +244,17 @@ __global__ void csa_shift_gather_kernel(const float* __restrict__ t, const float
 #pragma unroll
     for (int dxi = 0; dxi < 4; ++dxi) {
       const int x = X + dxi - 2;
-      if (x >= 0 && x < Wp) add(bi + (long long)x * nc + dxi * C + co, -1.0f);
+      if (x >= 0 && x < Wp) add_parts(bi + (long long)x * nc + dxi * C + co, -1.0f);
     }
   }
   if (X == 0) {
 #pragma unroll
     for (int dyi = 0; dyi < 4; ++dyi) {
       const int y = Y + dyi - 2;
-      if (y >= 0 && y < Hp) add(bi + (long long)(Wp + y) * nc + (4 + dyi) * C + co, -1.0f);
+      if (y >= 0 && y < Hp) add_parts(bi + (long long)(Wp + y) * nc + (4 + dyi) * C + co, -1.0f);
     }
   }
-  if (Y == 0 && X == 0) add(bi + 8 * C + co, 1.0f);
+  if (Y == 0 && X == 0) add_parts(bi + 8 * C + co, 1.0f);
   const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co));
   const float r0 = __fdiv_rn(acc.x + b4.x, 6.0f), r1 = __fdiv_rn(acc.y + b4.y, 6.0f);
   const float r2 = __fdiv_rn(acc.z + b4.z, 6.0f), r3 = __fdiv_rn(acc.w + b4.w, 6.0f);
@@ -368,6 +372,7 @@ struct CsaTcSizes {
   int Chp, ldP, ldQ;                                // ldP: row stride of the split P matrices (16-bit elements, 16-byte rows)
   int He, We, rows_b;                               // extended key grid of G; boundary query rows per image (x128)
   int kq_slabs, kq_units, vt_slabs, vt_units, vc_units;
+  int csplit;                                       // K parts of the boundary GEMM (it has few rows: split K to fill the GPU)
 };
 static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   CsaTcSizes s;
@@ -386,6 +391,14 @@ static CsaTcSizes csa_tc_sizes(int B, int H, int W, int C) {
   if (g > B) g = B;
   if (s.HWp % ROWS != 0) g = 1;
   s.group = (int)g;
+  {
+    const long long base_jobs = (long long)s.group * (s.rows_b / ROWS) * ((s.vc_units + 1) / 2);
+    long long want = 148 / (base_jobs > 0 ? base_jobs : 1);
+    if (want > s.vt_slabs / 4) want = s.vt_slabs / 4;
+    if (want < 1) want = 1;
+    const int spp = (int)((s.vt_slabs + want - 1) / want);
+    s.csplit = (s.vt_slabs + spp - 1) / spp;        // every part non-empty
+  }
   return s;
 }
 
@@ -424,7 +437,7 @@ static CsaTcBufs csa_tc_carve(Arena& a, const PlanLayout& L, const CsaTcSizes& s
   b.Bh = a.take<split_t>((size_t)g * s.rows_b * s.ldP);
   b.Bl = a.take<split_t>((size_t)g * s.rows_b * s.ldP);
   b.T = a.take<float>((size_t)g * s.HWp * 16 * C);
-  b.Tb = a.take<float>((size_t)g * s.rows_b * 9 * C);
+  b.Tb = a.take<float>((size_t)s.csplit * g * s.rows_b * 9 * C);
   b.kblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.kq_slabs, s.kq_units));
   b.vblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.vt_slabs, s.vt_units));
   b.cblob = a.take<uint8_t>((size_t)g * tc_operand_blob_bytes(s.vt_slabs, s.vc_units));
@@ -500,11 +513,13 @@ int run_cs_attn_tc(const PlanLayout& L, const float* plan, const float* featT, i
     if ((rc = tma_make_map_2d(&bmap_hi, b.Bh, brows, s.ldP)) || (rc = tma_make_map_2d(&bmap_lo, b.Bl, brows, s.ldP))) return rc;
     if ((rc = tc_gemm(GemmShape{rows, s.vt_slabs, s.vt_units, s.HWp, vstride, csa_kchunk()}, b.vblob,
                       TmaRowsGen{}, OutEpi{b.T, 16 * C, 1.0f / CSA_P_SCALE}, st, &map_hi, &map_lo))) return rc;
-    if ((rc = tc_gemm(GemmShape{brows, s.vt_slabs, s.vc_units, s.rows_b, cstride, csa_kchunk()}, b.cblob,
-                      TmaRowsGen{}, OutEpi{b.Tb, 9 * C, 1.0f / CSA_P_SCALE}, st, &bmap_hi, &bmap_lo))) return rc;
+    GemmShape cshape{brows, s.vt_slabs, s.vc_units, s.rows_b, cstride, csa_kchunk()};
+    cshape.ksplit = s.csplit;                      // few rows, long K: K parts run as independent jobs
+    if ((rc = tc_gemm(cshape, b.cblob, TmaRowsGen{}, OutEpi{b.Tb, 9 * C, 1.0f / CSA_P_SCALE}, st, &bmap_hi, &bmap_lo)))
+      return rc;
     const long long otot = (long long)g * H * W * (C / 4);
     CIAOSR_LAUNCH(csa_shift_gather_kernel, cdiv(otot, 256), 256, 0, st, b.T, b.Tb, plan + L.down_b, out_nhwc, ldo,
-                  out_nchw, H, W, s.Hp, s.Wp, C, s.rows_b, (long long)i0, otot);
+                  out_nchw, H, W, s.Hp, s.Wp, C, s.rows_b, s.csplit, brows * 9LL * C, (long long)i0, otot);
   }
   return CIAOSR_OK;
 }

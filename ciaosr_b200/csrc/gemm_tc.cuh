@@ -22,6 +22,15 @@ struct GemmShape {
   long long rows_per_image;    // B operand switches every this many rows (M if shared)
   size_t blob_image_stride;    // bytes between per-image blobs (0 if shared)
   int kchunk = 0;              // K-slabs per accumulation chunk (0 = all of K in one TMEM accumulation), see below
+  int ksplit = 0;              // > 1 (TMA-fed A only): the K range is cut into `ksplit` parts that run as INDEPENDENT jobs
+                               // (few-row, long-K problems would otherwise occupy a handful of CTAs); part p stores its
+                               // partial product through the epilogue at virtual row  p * (m_tiles * 128) + m,  i.e. the
+                               // output is [ksplit][m_tiles * 128, N] and the caller sums the parts.
+  int a_resident = 0;          // 1: K fits the four operand slots (kslabs <= 4): A is generated ONCE per 128-row tile and
+                               // kept in shared memory while all N-chunks of that tile are issued back to back (the
+                               // epilogue of chunk c overlaps the UMMAs of chunk c+1 through the two accumulators).
+                               // Short-K layers (the SwinIR trunk's K = 180 / 360 Linears) are otherwise bound by
+                               // regenerating A and refilling the pipeline per (tile, chunk) job.
 };
 // Long-K accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with TRUNCATION (measured,
 // tools/ubench/mma_acc.cu: adding 0.94 ulp to 1.0 leaves 1.0; products inside one K16 instruction keep 2 guard
@@ -77,40 +86,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen agen, const Epi epi,
                const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
-  const uint32_t tmem_base = tc_prologue<1, TC_NEPI>(s, smem);
+  const TcShared s = tc_carve_gemm(smem);
+  const uint32_t tmem_base = tc_prologue<1, TC_NEPI>(s, smem, GM_SLOT);
   const int warp = threadIdx.x >> 5;
   const int m_tiles = (int)((g.M + ROWS - 1) / ROWS);
   const int n_chunks = (g.nunits + 1) / 2;
-  const long long n_jobs = (long long)m_tiles * n_chunks;
-
-  const int kchunk = (g.kchunk > 0 && g.kchunk < g.kslabs) ? g.kchunk : g.kslabs;
-  const int n_kc = (g.kslabs + kchunk - 1) / kchunk;
+  const bool resident = g.a_resident != 0;           // host guarantees: kslabs <= 4, no K chunking, no TMA-fed A
+  // outer job = (tile, first chunk): one chunk per job normally, all chunks of the tile in resident mode
+  const int cpj = resident ? n_chunks : 1;           // chunks per outer job
+  const int ksplit = g.ksplit > 1 ? g.ksplit : 1;
+  const int spp = (g.kslabs + ksplit - 1) / ksplit;  // K-slabs per part
+  const long long jobs_per_part = resident ? (long long)m_tiles : (long long)m_tiles * n_chunks;
+  const long long n_jobs = jobs_per_part * ksplit;
+  // K range of a job: slabs [k0, k0 + klen), accumulated in chunks of `kchunk` slabs
+  auto k_range = [&](long long job, int& k0, int& klen, int& kch, int& nkc) {
+    const int part = (int)(job / jobs_per_part);
+    k0 = part * spp;
+    klen = max(0, min(spp, g.kslabs - k0));
+    kch = (g.kchunk > 0 && g.kchunk < klen) ? g.kchunk : max(klen, 1);
+    nkc = (klen + kch - 1) / kch;
+  };
 
   if (warp == 0) {
     ProdState ps{0};
     uint32_t afree_bits = 0xFu;
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-      const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
-      const int units = min(2, g.nunits - 2 * nc);
+      const long long jb = job % jobs_per_part;
+      const int mt = (int)(resident ? jb : jb / n_chunks), nc0 = (int)(resident ? 0 : jb % n_chunks);
       const long long image = ((long long)mt * ROWS) / g.rows_per_image;
-      // blob order: for chunk: for slab: for unit
-      const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES;
-      for (int kc = 0; kc < n_kc; ++kc) {
-        const int ns = min(kchunk, g.kslabs - kc * kchunk);
-        if constexpr (agen_tma<AGen>::value)
-          produce_job_tma_a<1, TC_NEPI>(s, ps, afree_bits, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0,
-                                        &map_hi, &map_lo, kc * kchunk, mt * ROWS);
-        else
-          produce_job<1>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0);
+      int k0, klen, kchunk, n_kc;
+      k_range(job, k0, klen, kchunk, n_kc);
+      for (int nc = nc0; nc < nc0 + cpj; ++nc) {
+        const int units = min(2, g.nunits - 2 * nc);
+        // blob order: for chunk: for slab: for unit
+        const uint8_t* src = blob + image * g.blob_image_stride + (size_t)nc * 2 * g.kslabs * UNIT_BYTES +
+                             (size_t)k0 * units * UNIT_BYTES;
+        for (int kc = 0; kc < n_kc; ++kc) {
+          const int ns = min(kchunk, klen - kc * kchunk);
+          if constexpr (agen_tma<AGen>::value)
+            produce_job_tma_a<1, TC_NEPI, true>(s, ps, afree_bits, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns,
+                                                units, 0, &map_hi, &map_lo, k0 + kc * kchunk, mt * ROWS);
+          else
+            produce_job<1, true>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0);
+        }
       }
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-      const int nc = (int)(job % n_chunks);
-      for (int kc = 0; kc < n_kc; ++kc)
-        mma_job<1>(s, tmem_base, m, min(kchunk, g.kslabs - kc * kchunk), min(2, g.nunits - 2 * nc), true);
+      const long long jb = job % jobs_per_part;
+      const int nc0 = (int)(resident ? 0 : jb % n_chunks);
+      int k0, klen, kchunk, n_kc;
+      k_range(job, k0, klen, kchunk, n_kc);
+      for (int nc = nc0; nc < nc0 + cpj; ++nc)
+        for (int kc = 0; kc < n_kc; ++kc)
+          mma_job<1, true>(s, tmem_base, m, min(kchunk, klen - kc * kchunk), min(2, g.nunits - 2 * nc),
+                           !resident || nc == 0, !resident || nc == n_chunks - 1);
     }
   } else if (warp >= 4) {
     const int half = (warp - 4) >> 2;
@@ -118,48 +149,56 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     EpiState e{0, 0xFu, 0};
     for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-      const int mt = (int)(job / n_chunks), nc = (int)(job % n_chunks);
-      const int units = min(2, g.nunits - 2 * nc);
+      const long long jb = job % jobs_per_part;
+      const int mt = (int)(resident ? jb : jb / n_chunks), nc0 = (int)(resident ? 0 : jb % n_chunks);
       const long long m = (long long)mt * ROWS + row;
       const bool valid = m < g.M;
+      const long long m_out = m + (job / jobs_per_part) * ((long long)m_tiles * ROWS);     // part-stacked output rows
+      int k0, klen, kchunk, n_kc;
+      k_range(job, k0, klen, kchunk, n_kc);
       typename AGen::Row rs = agen.row(valid ? m : 0);
-      for (int kc = 0; kc < n_kc; ++kc) {
-        const int sl_end = min((kc + 1) * kchunk, g.kslabs);
+      for (int nc = nc0; nc < nc0 + cpj; ++nc) {
+        const int units = min(2, g.nunits - 2 * nc);
+        for (int kc = 0; kc < n_kc; ++kc) {
+          const int sl_end = k0 + min((kc + 1) * kchunk, klen);
+          if (!resident || nc == 0) {
 #pragma unroll 1
-        for (int sl = kc * kchunk; sl < sl_end; ++sl) {
-          const int slot = sl & 3;
-          if constexpr (agen_tma<AGen>::value) { e.afree_bits ^= 1u << slot; continue; }   // producer-loaded slab
-          float v[32];
-          if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
-          else {
+            for (int sl = k0 + kc * kchunk; sl < sl_end; ++sl) {
+              const int slot = (sl - k0) & 3;
+              if constexpr (agen_tma<AGen>::value) { e.afree_bits ^= 1u << slot; continue; }   // producer-loaded slab
+              float v[32];
+              if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
+              else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+              }
+              slab_begin(s, e, slot, true);
+              a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+              slab_done(s, slot);
+            }
           }
-          slab_begin(s, e, slot, true);
-          a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
-          slab_done(s, slot);
-        }
-        if constexpr (agen_combines<AGen>::value) {
-          if (kc == n_kc - 1) {
-            s.xchg[half * ROWS + row] = agen.partial(rs);
-            epi_sync<TC_NEPI>();
-            agen.partial(rs) = s.xchg[row] + s.xchg[ROWS + row];
+          if constexpr (agen_combines<AGen>::value) {
+            if (kc == n_kc - 1) {
+              s.xchg[half * ROWS + row] = agen.partial(rs);
+              epi_sync<TC_NEPI>();
+              agen.partial(rs) = s.xchg[row] + s.xchg[ROWS + row];
+            }
           }
-        }
-        const uint32_t d = epi_wait_d(s, e, units);
+          const uint32_t d = epi_wait_d(s, e, units);
 #pragma unroll 1
-        for (int cc = half; cc < units * 4; cc += 2) {
-          float v[32];
-          tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
-          if (valid) {
-            if (kc == 0) epi.store(rs, m, nc * 256 + cc * 32, v);
-            else if constexpr (epi_accumulates<Epi, typename AGen::Row>::value)
-              epi.accumulate(rs, m, nc * 256 + cc * 32, v);
+          for (int cc = half; cc < units * 4; cc += 2) {
+            float v[32];
+            tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
+            if (valid) {
+              if (kc == 0) epi.store(rs, m_out, nc * 256 + cc * 32, v);
+              else if constexpr (epi_accumulates<Epi, typename AGen::Row>::value)
+                epi.accumulate(rs, m_out, nc * 256 + cc * 32, v);
+            }
           }
+          epi_release_d(s, e);
         }
-        epi_release_d(s, e);
+        if constexpr (agen_combines<AGen>::value) epi_sync<TC_NEPI>();     // xchg is rewritten by the next job
       }
-      if constexpr (agen_combines<AGen>::value) epi_sync<TC_NEPI>();     // xchg is rewritten by the next job
     }
   }
   tc_teardown<1>(tmem_base);
@@ -179,14 +218,19 @@ static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, co
   CIAOSR_REQUIRE(!agen_tma<AGen>::value || (map_hi && map_lo), CIAOSR_E_INVALID, "tc_gemm: tensor maps missing");
   static const CUtensorMap no_map = {};
   static DynSmemOptIn optin;         // one per template instantiation, per device (common.cuh)
-  if (int rc = optin.ensure(tc_gemm_kernel<AGen, Epi>, SM_TOTAL)) return rc;
-  const long long n_jobs = ((g.M + ROWS - 1) / ROWS) * ((g.nunits + 1) / 2);
+  if (int rc = optin.ensure(tc_gemm_kernel<AGen, Epi>, GM_TOTAL)) return rc;
+  const long long n_jobs = ((g.M + ROWS - 1) / ROWS) * (g.a_resident ? 1 : (g.nunits + 1) / 2) * (g.ksplit > 1 ? g.ksplit : 1);
+  CIAOSR_REQUIRE(g.ksplit <= 1 || (agen_tma<AGen>::value && !g.a_resident), CIAOSR_E_INVALID,
+                 "tc_gemm: K splitting needs a TMA-fed A operand");
+  CIAOSR_REQUIRE(!g.a_resident || (g.kslabs <= 4 && !(g.kchunk > 0 && g.kchunk < g.kslabs) && !agen_tma<AGen>::value &&
+                                   !agen_combines<AGen>::value),
+                 CIAOSR_E_INVALID, "tc_gemm: A-resident mode needs K <= 256, one accumulation pass and a generated A");
   if (g.kchunk > 0 && g.kchunk < g.kslabs) {
     const bool can = epi_accumulates<Epi, typename AGen::Row>::value;
     CIAOSR_REQUIRE(can && g.kchunk % 4 == 0, CIAOSR_E_INVALID,
                    "tc_gemm: K chunking needs an accumulating epilogue and kchunk %% 4 == 0 (operand slots)");
   }
-  CIAOSR_LAUNCH((tc_gemm_kernel<AGen, Epi>), tc_grid_size(n_jobs), TC_THREADS, SM_TOTAL, st, g, blob, agen, epi,
+  CIAOSR_LAUNCH((tc_gemm_kernel<AGen, Epi>), tc_grid_size(n_jobs), TC_THREADS, GM_TOTAL, st, g, blob, agen, epi,
                 map_hi ? *map_hi : no_map, map_lo ? *map_lo : no_map);
   return CIAOSR_OK;
 }

@@ -33,10 +33,12 @@ struct LinSrc {            // B[n, k] = W[n, k]
   const float* w; int K;
   __device__ __forceinline__ float operator()(int, int n, int k) const { return w[(long long)n * K + k]; }
 };
-struct LinEpi {            // out[m, n] = act(acc + bias[n]), N % 4 == 0
-  float* o; const float* bias; int N; int act;
-  __device__ __forceinline__ void store(const LinRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
+struct LinEpi {            // out[m, n] = act(acc + bias[n]) (+ res[m, n]), N % 4 == 0
+  float* o; const float* bias; int N; int act; const float* res;
+  template <class Row>
+  __device__ __forceinline__ void store(const Row&, long long m, int n0, const float (&v)[32]) const {
     float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
+    const float4* rsrc = res ? reinterpret_cast<const float4*>(res + m * N + n0) : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = n0 + 4 * j;
@@ -46,10 +48,56 @@ struct LinEpi {            // out[m, n] = act(acc + bias[n]), N % 4 == 0
       for (int i = 0; i < 4; ++i) {
         float a = v[4 * j + i] + (bias ? __ldg(bias + n + i) : 0.0f);
         if (act == 1) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));      // nn.GELU() (exact)
+        else if (act == 2) a = fmaxf(a, 0.0f);                                         // nn.ReLU()
         t[i] = a;
       }
+      if (rsrc) { const float4 r = __ldg(rsrc + j); t[0] += r.x; t[1] += r.y; t[2] += r.z; t[3] += r.w; }
       dst[j] = make_float4(t[0], t[1], t[2], t[3]);
     }
+  }
+};
+
+// 3x3 convolution, stride 1, zero padding 1, on an NHWC map as an implicit GEMM: A[(b,y,x), k = t*Cin + ci] gathered
+// from the map (t = ky*3 + kx; Cin % 4 == 0, so a float4 never straddles a tap), B[co, k] = weight[co, ci, ky, kx].
+// The RSTB / trunk convolutions of SwinIR (swinir_net.py:446-483, 706-713) act on token tensors [B, HW, C], which ARE
+// NHWC maps: no patch_unembed / patch_embed transposes, and the RSTB's residual rides in the epilogue.
+struct Conv3Gen {
+  const float* x; int H, W, C;
+  struct Row { int y, x; };
+  __device__ __forceinline__ Row row(long long m) const {
+    const int hw = (int)(m % ((long long)H * W));
+    return Row{hw / W, hw % W};
+  }
+  __device__ __forceinline__ void fill(Row& r, long long m, int k0, float (&v)[32]) const {
+    const float* src[8];
+    bool ok[8];
+    const float* self = x + m * C;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k = k0 + 4 * g;
+      src[g] = self; ok[g] = false;
+      if (k < 9 * C) {
+        const int t = k / C, ch = k - t * C;
+        const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
+        ok[g] = r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W;
+        if (ok[g]) src[g] = self + (dy * W + dx) * C + ch;
+      }
+    }
+    float4 q[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
+      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
+    }
+  }
+};
+struct Conv3Src {          // B[n = co, k = t*Cin + ci] = weight[co, ci, t]
+  const float* w; int Cin;
+  __device__ __forceinline__ float operator()(int, int n, int k) const {
+    const int t = k / Cin, ci = k - t * Cin;
+    return w[((long long)n * Cin + ci) * 9 + t];
   }
 };
 
@@ -96,10 +144,67 @@ int ciaosr_linear_forward(const ciaosr_linear_desc* d, const void* plan, const f
   CIAOSR_REQUIRE(rows >= 0 && (activation == 0 || activation == 1), CIAOSR_E_INVALID,
                  "linear: bad rows=%lld or activation=%d", rows, activation);
   if (rows == 0) return CIAOSR_OK;
+  return ciaosr_linear_forward_res(d, plan, x, rows, activation, nullptr, out, stream);
+}
+
+int ciaosr_linear_forward_res(const ciaosr_linear_desc* d, const void* plan, const float* x, long long rows,
+                              int activation, const float* residual, float* out, void* stream) {
+  int rc = lin_check(d);
+  if (rc) return rc;
+  CIAOSR_REQUIRE(plan && x && out, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(rows >= 0 && activation >= 0 && activation <= 2, CIAOSR_E_INVALID,
+                 "linear: bad rows=%lld or activation=%d", rows, activation);
+  if (rows == 0) return CIAOSR_OK;
   StageScope sc(6, (cudaStream_t)stream);
   const int kslabs = (d->in_features + KSLAB - 1) / KSLAB, nunits = (d->out_features + UNIT_N - 1) / UNIT_N;
+  GemmShape g{rows, kslabs, nunits, rows, 0};
+  g.a_resident = (kslabs <= 4 && nunits > 2) ? 1 : 0;        // short K, several N-chunks: generate A once per tile
+  return tc_gemm(g, reinterpret_cast<const uint8_t*>(plan), LinRowsGen{x, d->in_features},
+                 LinEpi{out, d->bias, d->out_features, activation, residual}, (cudaStream_t)stream);
+}
+
+static int conv_check(const ciaosr_conv3x3_desc* d) {
+  CIAOSR_REQUIRE(d != nullptr, CIAOSR_E_INVALID, "desc is NULL");
+  CIAOSR_REQUIRE(d->abi_version == CIAOSR_ABI_VERSION, CIAOSR_E_INVALID, "ABI version mismatch");
+  CIAOSR_REQUIRE(d->in_channels > 0 && d->out_channels > 0 && d->in_channels % 4 == 0 && d->out_channels % 4 == 0,
+                 CIAOSR_E_INVALID, "conv3x3: channel counts must be positive multiples of 4, got %d -> %d",
+                 d->in_channels, d->out_channels);
+  CIAOSR_REQUIRE(d->weight != nullptr, CIAOSR_E_INVALID, "conv3x3: weight is NULL");
+  return CIAOSR_OK;
+}
+
+int ciaosr_conv3x3_plan_bytes(const ciaosr_conv3x3_desc* d, size_t* bytes) {
+  CIAOSR_REQUIRE(bytes != nullptr, CIAOSR_E_INVALID, "bytes is NULL");
+  int rc = conv_check(d);
+  if (rc) return rc;
+  *bytes = tc_operand_blob_bytes((9 * d->in_channels + KSLAB - 1) / KSLAB, (d->out_channels + UNIT_N - 1) / UNIT_N);
+  return CIAOSR_OK;
+}
+
+int ciaosr_conv3x3_plan_init(const ciaosr_conv3x3_desc* d, void* plan, size_t plan_bytes, void* stream) {
+  int rc = conv_check(d);
+  if (rc) return rc;
+  size_t need = 0;
+  ciaosr_conv3x3_plan_bytes(d, &need);
+  CIAOSR_REQUIRE(plan != nullptr && ((uintptr_t)plan % 256) == 0 && plan_bytes >= need, CIAOSR_E_WORKSPACE,
+                 "conv3x3 plan buffer too small or misaligned: need %zu, have %zu", need, plan_bytes);
+  return tc_pack_operand(reinterpret_cast<uint8_t*>(plan), 1, d->out_channels, 9 * d->in_channels, 0,
+                         Conv3Src{d->weight, d->in_channels}, (cudaStream_t)stream);
+}
+
+int ciaosr_conv3x3_nhwc_forward(const ciaosr_conv3x3_desc* d, const void* plan, const float* x, int B, int H, int W,
+                                int activation, const float* residual, float* out, void* stream) {
+  int rc = conv_check(d);
+  if (rc) return rc;
+  CIAOSR_REQUIRE(plan && x && out, CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(B >= 0 && H > 0 && W > 0 && (activation == 0 || activation == 2), CIAOSR_E_INVALID,
+                 "conv3x3: bad shape B=%d H=%d W=%d or activation=%d (0 none, 2 ReLU)", B, H, W, activation);
+  if (B == 0) return CIAOSR_OK;
+  StageScope sc(6, (cudaStream_t)stream);
+  const long long rows = (long long)B * H * W;
+  const int kslabs = (9 * d->in_channels + KSLAB - 1) / KSLAB, nunits = (d->out_channels + UNIT_N - 1) / UNIT_N;
   return tc_gemm(GemmShape{rows, kslabs, nunits, rows, 0}, reinterpret_cast<const uint8_t*>(plan),
-                 LinRowsGen{x, d->in_features}, LinEpi{out, d->bias, d->out_features, activation},
+                 Conv3Gen{x, H, W, d->in_channels}, LinEpi{out, d->bias, d->out_channels, activation, residual},
                  (cudaStream_t)stream);
 }
 

@@ -42,8 +42,17 @@ constexpr int SM_CONST = SM_W + W_STAGES * SLAB_BYTES;  // floats: per-kernel co
 constexpr int CONST_FLOATS = 16 * HID + 2048;
 constexpr int SM_BAR = SM_CONST + CONST_FLOATS * 4;
 constexpr int BAR_W_FULL = 0, BAR_W_EMPTY = 4, BAR_A_READY = 8, BAR_A_FREE = 12, BAR_D_READY = 16,
-              BAR_D_FREE = 20, N_BARS = 22;     // D_READY[d][n-half]: 16 + 2 d + nh
+              BAR_D_FREE = 20, BAR_W_FULL2 = 22, BAR_W_EMPTY2 = 24, N_BARS = 26;     // D_READY[d][n-half]: 16 + 2 d + nh
+// Ring stages 4, 5 (W2 = true only): a SECOND pair of W_hi stages.  The hi stages of a K-slab are read by 8 of its
+// 12 UMMAs, so with one pair they are free for only ~1/3 of a slab's issue time -- less than the L2 -> smem latency
+// of the next slab's 32 KB, which stalled the issuer on W_FULL (round 1: 4.1 k cycles per slab against 2.3 k of
+// UMMA issue in the long-K GEMMs).  Alternating two hi pairs gives every hi load a whole slab of slack; the lo pair
+// (4 UMMAs per slab) already had 2/3 of a slab.  Used by tc_gemm (which has no per-kernel constants and can afford
+// the extra 32 KB); the head kernels keep the 4-stage ring.
+__host__ __device__ constexpr int w_full_bar(int stage) { return stage < 4 ? BAR_W_FULL + stage : BAR_W_FULL2 + stage - 4; }
+__host__ __device__ constexpr int w_empty_bar(int stage) { return stage < 4 ? BAR_W_EMPTY + stage : BAR_W_EMPTY2 + stage - 4; }
 constexpr int SM_SLOT = SM_BAR + N_BARS * 8;            // TMEM base address (4 B, padded to 16)
+static_assert(SM_BAR + N_BARS * 8 + 16 + 1024 * 4 <= 227 * 1024, "head kernels' shared memory exceeds 227 KB");
 constexpr int SM_XCHG = SM_SLOT + 16;                   // 1024 floats of row-thread exchange space
 constexpr int SM_TOTAL = SM_XCHG + 1024 * 4;
 constexpr int EPI_T0 = 128;                             // first row thread (warps 0..3 are control warps)
@@ -66,22 +75,39 @@ __device__ __forceinline__ TcShared tc_carve(uint8_t* smem) {
 __device__ __forceinline__ uint32_t bar_at(const TcShared& s, int i) { return s.bar + 8u * i; }
 
 // common prologue: barrier init + TMEM allocation; returns the TMEM base address
+// smem layout of tc_gemm (gemm_tc.cuh): no per-kernel constants, six ring stages (two W_hi pairs, see w_full_bar)
+constexpr int GM_W_STAGES = 6;
+constexpr int GM_BAR = SM_W + GM_W_STAGES * SLAB_BYTES;
+constexpr int GM_SLOT = GM_BAR + N_BARS * 8;
+constexpr int GM_XCHG = GM_SLOT + 16;                   // 256 floats: the two partial sums per row of combining AGens
+constexpr int GM_TOTAL = GM_XCHG + 256 * 4;
+static_assert(GM_TOTAL <= 227 * 1024, "tc_gemm shared memory exceeds the 227 KB a CTA may opt in to");
+__device__ __forceinline__ TcShared tc_carve_gemm(uint8_t* smem) {
+  TcShared s;
+  const uint32_t base = smem_u32(smem);
+  s.a_hi = base + SM_A_HI; s.a_lo = base + SM_A_LO; s.w = base + SM_W;
+  s.bar = base + GM_BAR;
+  s.consts = nullptr;
+  s.xchg = reinterpret_cast<float*>(smem + GM_XCHG);
+  return s;
+}
+
 template <int CL, int NEPI>
-__device__ __forceinline__ uint32_t tc_prologue(const TcShared& s, uint8_t* smem) {
+__device__ __forceinline__ uint32_t tc_prologue(const TcShared& s, uint8_t* smem, int slot_off = SM_SLOT) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < W_STAGES; ++i) { mbar_init(bar_at(s, BAR_W_FULL + i), 1); mbar_init(bar_at(s, BAR_W_EMPTY + i), CL); }
+    for (int i = 0; i < W_STAGES + 2; ++i) { mbar_init(bar_at(s, w_full_bar(i)), 1); mbar_init(bar_at(s, w_empty_bar(i)), CL); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar_at(s, BAR_A_READY + i), NEPI / 32); mbar_init(bar_at(s, BAR_A_FREE + i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(bar_at(s, BAR_D_READY + i), 1);
     for (int i = 0; i < 2; ++i) mbar_init(bar_at(s, BAR_D_FREE + i), NEPI / 32);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(smem) + SM_SLOT, 512);
+  if (warp == 2) tmem_alloc(smem_u32(smem) + slot_off, 512);
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();          // peer barriers are initialised before any multicast reaches them
   tc_fence_after();
-  return *reinterpret_cast<volatile uint32_t*>(smem + SM_SLOT);
+  return *reinterpret_cast<volatile uint32_t*>(smem + slot_off);
 }
 template <int CL>
 __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
@@ -96,24 +122,29 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
 //   stage 0 = W_hi rows   0..127, stage 1 = W_hi rows 128..255   (adjacent: one N = 256 B operand)
 //   stage 2 = W_lo rows   0..127, stage 3 = W_lo rows 128..255
 // Jobs with a single 128-column unit leave stages 1 and 3 empty (plain arrive, no bytes).
-struct ProdState { uint32_t phase; };
+// bits: per ring stage, the parity of its NEXT use (0 on a fresh barrier); slabs: K-slabs streamed so far (the hi
+// pair alternates with it when W2).  The first member keeps its old name / meaning for the 4-stage users.
+struct ProdState { uint32_t bits; uint32_t slabs; };
 
 // stream the weights of one job: units are stored (K-slab major) as [hi slab][lo slab] pairs
-template <int CL>
+template <int CL, bool W2 = false>
 __device__ __forceinline__ void produce_job(const TcShared& s, ProdState& ps, const uint8_t* blob, int nslabs,
                                             int units, uint32_t cta_rank) {
   const bool leader = (threadIdx.x & 31) == 0;
   for (int sl = 0; sl < nslabs; ++sl) {
+    const int hi0 = (W2 && (ps.slabs & 1)) ? 4 : 0;
 #pragma unroll
     for (int part = 0; part < 4; ++part) {
       const int u = part & 1, lo = part >> 1;
-      mbar_wait(bar_at(s, BAR_W_EMPTY + part), ps.phase ^ 1, 100 + part);
+      const int stage = lo ? part : hi0 + part;
+      mbar_wait(bar_at(s, w_empty_bar(stage)), ((ps.bits >> stage) & 1) ^ 1, 100 + stage);
+      ps.bits ^= 1u << stage;
       if (leader) {
-        const uint32_t full = bar_at(s, BAR_W_FULL + part);
+        const uint32_t full = bar_at(s, w_full_bar(stage));
         if (u < units) {
           mbar_arrive_expect_tx(full, SLAB_BYTES);
           const uint8_t* src = blob + ((size_t)(sl * units + u) * 2 + lo) * SLAB_BYTES;
-          const uint32_t dst = s.w + part * SLAB_BYTES;
+          const uint32_t dst = s.w + stage * SLAB_BYTES;
           if (CL == 1) bulk_g2s(dst, src, SLAB_BYTES, full);
           else if ((uint32_t)u == cta_rank) bulk_g2s_mc(dst, src, SLAB_BYTES, full, (uint16_t)((1u << CL) - 1));
         } else {
@@ -122,7 +153,7 @@ __device__ __forceinline__ void produce_job(const TcShared& s, ProdState& ps, co
       }
       __syncwarp();
     }
-    ps.phase ^= 1;
+    ++ps.slabs;
   }
 }
 
@@ -132,7 +163,7 @@ __device__ __forceinline__ void produce_job(const TcShared& s, ProdState& ps, co
 // slabs.  A slabs run up to 3 ahead of the weights (4 operand slots): the warp blocks only for the slab it
 // needs now.  A_READY counts NEPI/32 arrivals (row-warp-written slabs); for a TMA slab the producer supplies
 // all of them itself, one carrying the transaction byte count.  `afree_bits`: parity to wait on next per slot.
-template <int CL, int NEPI>
+template <int CL, int NEPI, bool W2 = false>
 __device__ __forceinline__ void produce_job_tma_a(const TcShared& s, ProdState& ps, uint32_t& afree_bits,
                                                   const uint8_t* blob, int nslabs, int units, uint32_t cta_rank,
                                                   const CUtensorMap* map_hi, const CUtensorMap* map_lo, int kslab0,
@@ -156,12 +187,13 @@ __device__ __forceinline__ void produce_job_tma_a(const TcShared& s, ProdState& 
       __syncwarp();
       ++a_next;
     }
-    produce_job<CL>(s, ps, blob + (size_t)sl * units * UNIT_BYTES, 1, units, cta_rank);
+    produce_job<CL, W2>(s, ps, blob + (size_t)sl * units * UNIT_BYTES, 1, units, cta_rank);
   }
 }
 
 // ---- UMMA issuer (warp 1; the whole warp walks the loop, lane 0 issues and commits) -------------------
-struct MmaState { uint32_t wphase; uint32_t jobctr; uint32_t aready_bits; };
+// wbits: per ring stage, the parity of the W_FULL completion to wait for next; slabs: K-slabs issued so far
+struct MmaState { uint32_t wbits; uint32_t jobctr; uint32_t aready_bits; uint32_t slabs = 0; };
 
 // descriptor for a slab at smem address `addr` (+ k-step offset): only the low word varies
 constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
@@ -180,25 +212,29 @@ __device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo32, uint32
 
 template <int CL>
 __device__ __forceinline__ void release_stage(const TcShared& s, int stage) {
-  if (CL == 1) umma_commit(bar_at(s, BAR_W_EMPTY + stage));
-  else umma_commit_mc(bar_at(s, BAR_W_EMPTY + stage), (uint16_t)((1u << CL) - 1));
+  if (CL == 1) umma_commit(bar_at(s, w_empty_bar(stage)));
+  else umma_commit_mc(bar_at(s, w_empty_bar(stage)), (uint16_t)((1u << CL) - 1));
 }
 
 // one job: D[jobctr & 1][:, 0 : 128*units) = A (nslabs x 64 K) * W^T ; A slabs cycle through the 4 smem slots.
 // One UMMA covers all 128*units columns (N = 256 for full jobs): 12 instructions per K-slab, each worth
 // 128 tensor-core cycles, so the single issuing thread is never the bottleneck.
-template <int CL>
+// a_release = false: the A slabs stay in their slots for the next job (same rows, next N-chunk); A_FREE is then
+// committed only by the last job that reads them, so waiters see exactly one completion per slot use.
+template <int CL, bool W2 = false>
 __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, MmaState& m, int nslabs,
-                                        int units, bool a_new) {
+                                        int units, bool a_new, bool a_release = true) {
   const bool leader = (threadIdx.x & 31) == 0;
   const uint32_t idesc = make_idesc_split(ROWS, UNIT_N * units);
   const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
   mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
   tc_fence_after();
   const uint32_t dcol = tmem_base + d * 256;
-  const uint32_t b_hi = desc_lo(s.w), b_lo = desc_lo(s.w + 2 * SLAB_BYTES);
+  const uint32_t b_lo = desc_lo(s.w + 2 * SLAB_BYTES);
   for (int sl = 0; sl < nslabs; ++sl) {
     const int slot = sl & 3;
+    const int hi0 = (W2 && (m.slabs & 1)) ? 4 : 0;
+    const uint32_t b_hi = desc_lo(s.w + hi0 * SLAB_BYTES);
     if (a_new) {
       mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
       m.aready_bits ^= 1u << slot;
@@ -206,8 +242,9 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
     TC_TRACE(1000 + sl);          // issuer: operand slab sl available
     const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
     // W_hi (stages 0,1): A_lo.W_hi (small term first) and A_hi.W_hi
-    mbar_wait(bar_at(s, BAR_W_FULL + 0), m.wphase, 220);
-    mbar_wait(bar_at(s, BAR_W_FULL + 1), m.wphase, 221);
+    mbar_wait(bar_at(s, w_full_bar(hi0)), (m.wbits >> hi0) & 1, 220);
+    mbar_wait(bar_at(s, w_full_bar(hi0 + 1)), (m.wbits >> (hi0 + 1)) & 1, 221);
+    m.wbits ^= 3u << hi0;
     tc_fence_after();
     if (leader) {
 #pragma unroll
@@ -215,23 +252,24 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
         umma_lo(dcol, a_lo + 2 * ks, b_hi + 2 * ks, idesc, (sl | ks) != 0 ? 1u : 0u);
         umma_lo(dcol, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
       }
-      release_stage<CL>(s, 0);
-      release_stage<CL>(s, 1);
+      release_stage<CL>(s, hi0);
+      release_stage<CL>(s, hi0 + 1);
     }
     __syncwarp();
     // W_lo (stages 2,3): A_hi.W_lo
-    mbar_wait(bar_at(s, BAR_W_FULL + 2), m.wphase, 222);
-    mbar_wait(bar_at(s, BAR_W_FULL + 3), m.wphase, 223);
+    mbar_wait(bar_at(s, BAR_W_FULL + 2), (m.wbits >> 2) & 1, 222);
+    mbar_wait(bar_at(s, BAR_W_FULL + 3), (m.wbits >> 3) & 1, 223);
+    m.wbits ^= 3u << 2;
     tc_fence_after();
     if (leader) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) umma_lo(dcol, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
       release_stage<CL>(s, 2);
       release_stage<CL>(s, 3);
-      umma_commit(bar_at(s, BAR_A_FREE + slot));
+      if (a_release) umma_commit(bar_at(s, BAR_A_FREE + slot));
     }
     __syncwarp();
-    m.wphase ^= 1;
+    ++m.slabs;
   }
   if (leader) {
     umma_commit(bar_at(s, BAR_D_READY + 2 * d));

@@ -271,8 +271,38 @@ class LocalImplicitSREDSR(LocalImplicitSRNet):
         self.body = self.encoder.body
         self.conv_after_body = self.encoder.conv_after_body
         del self.encoder
+        # encoder fast path: the 64 -> 64 convolutions of the residual trunk as implicit GEMMs on the
+        # tensor cores with fp32-grade accuracy (csrc/linear_tc.cu: ciaosr_conv3x3_nhwc_forward, ReLU / residual fused).
+        # 'auto' = on for CUDA inference; False keeps the PyTorch / cuDNN trunk of the reference.
+        self.native_encoder = "auto"
+
+    def _gen_feature_native(self, x):
+        """ciaosr_net.py:393-408 on NHWC maps: conv_first stays in PyTorch (3 input channels; strict fp32), every
+        other convolution runs natively; None when a layer is outside what the native path supports."""
+        plans = []
+        for blk in self.body:
+            p1, p2 = native.conv3x3_plan_for(blk.conv1), native.conv3x3_plan_for(blk.conv2)
+            if p1 is None or p2 is None or float(getattr(blk, "res_scale", 1.0)) != 1.0:
+                return None
+            plans.append((p1, p2))
+        last = native.conv3x3_plan_for(self.conv_after_body)
+        if last is None:
+            return None
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            first = self.conv_first(x).permute(0, 2, 3, 1).contiguous()               # [B, H, W, C]
+        t = first
+        for p1, p2 in plans:
+            t = p2.forward(p1.forward(t, relu=True), residual=t)                      # x + conv2(relu(conv1(x)))
+        return last.forward(t, residual=first).permute(0, 3, 1, 2)
 
     def gen_feature(self, x):
+        if self.native_encoder and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
+            res = self._gen_feature_native(x)
+            if res is not None:
+                return [res]
+        if self.native_encoder is True:
+            raise RuntimeError("native_encoder=True needs a CUDA fp32 input, no_grad, and 3x3 / stride-1 / res_scale-1 "
+                               "convolutions with channel counts that are multiples of 4")
         x = self.conv_first(x)
         res = self.conv_after_body(self.body(x))
         res += x
@@ -302,7 +332,8 @@ class LocalImplicitSRSWINIR(LocalImplicitSRNet):
         x = self.pos_drop(self.patch_embed(x))
         for layer in self.layers:
             x = layer(x, x_size)
-        return self.patch_unembed(self.norm(x), x_size)
+        from . import swinir
+        return self.patch_unembed(swinir._norm(x, self.norm), x_size)
 
     def gen_feature(self, img):
         _, _, h, w = img.size()
@@ -311,6 +342,25 @@ class LocalImplicitSRSWINIR(LocalImplicitSRNet):
         from . import swinir
         x = self.conv_first(F.pad(img, (0, pad_w, 0, pad_h), "reflect"))
         with swinir.native_linear(bool(self.native_encoder) and img.is_cuda and not torch.is_grad_enabled()):
-            res = self.conv_after_body(self.forward_features(x))
-        res += x
+            res = self._after_body_native(x)
+            if res is None:
+                res = self.conv_after_body(self.forward_features(x))
+                res += x
         return [res[:, :, :h, :w]]
+
+    def _after_body_native(self, x):
+        """conv_after_body(forward_features(x)) + x with the 3x3 convolution on the token tensor (an NHWC map) through
+        the native implicit-GEMM path; None when that path does not apply (then the PyTorch ops above run)."""
+        from . import swinir
+        if not (swinir._NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+                and isinstance(self.conv_after_body, nn.Conv2d) and native.Conv3x3Plan.supports(self.conv_after_body)):
+            return None
+        x_size = (x.shape[2], x.shape[3])
+        t = self.pos_drop(self.patch_embed(x))
+        for layer in self.layers:
+            t = layer(t, x_size)
+        y = swinir._conv3x3_tokens(swinir._norm(t, self.norm), x_size, self.conv_after_body,
+                                   residual=x.permute(0, 2, 3, 1))
+        if y is None:
+            return None
+        return y.view(x.shape[0], x_size[0], x_size[1], -1).permute(0, 3, 1, 2)

@@ -212,6 +212,39 @@ def tile_blend_finish(acc, cnt, mean=None, std=None, clamp01=False):
     return out
 
 
+def window_attention_supported(c, heads, ws):
+    return heads > 0 and c % heads == 0 and c // heads <= 32 and ws * ws * heads <= 384
+
+
+def window_attention(qkv, bias_table, h, w, heads, ws, shift, scale):
+    """qkv [B, H*W, 3C] (natural token order) -> [B, H*W, C]: shifted-window multi-head attention with relative
+    position bias and SW-MSA mask (ciaosr_window_attention_forward)."""
+    qkv, bias_table = _f32c(qkv, "qkv"), _f32c(bias_table.detach(), "relative_position_bias_table")
+    b, n, c3 = qkv.shape
+    if n != h * w or c3 % 3:
+        raise ValueError(f"qkv must be [B, {h * w}, 3C], got {tuple(qkv.shape)}")
+    c = c3 // 3
+    if tuple(bias_table.shape) != ((2 * ws - 1) ** 2, heads):
+        raise ValueError(f"bias table must be [{(2 * ws - 1) ** 2}, {heads}], got {tuple(bias_table.shape)}")
+    out = torch.empty(b, n, c, dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().ciaosr_window_attention_forward(
+            _ptr(qkv), _ptr(bias_table), b, h, w, c, heads, ws, shift, float(scale), _ptr(out), _stream(qkv.device)))
+    return out
+
+
+def layernorm(x, ln):
+    """nn.LayerNorm over the last dim of a contiguous fp32 CUDA tensor (ciaosr_layernorm_forward)."""
+    x = _f32c(x, "x")
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ciaosr_layernorm_forward(
+            _ptr(x), _ptr(_f32c(ln.weight.detach(), "weight")), _ptr(_f32c(ln.bias.detach(), "bias")), float(ln.eps),
+            x.numel() // c, c, _ptr(out), _stream(x.device)))
+    return out
+
+
 def profile_enable(on=True):
     """Bracket the library's stages with CUDA events (see ciaosr_profile_read)."""
     _lib.check(_lib.load().ciaosr_profile_enable(1 if on else 0))
@@ -338,15 +371,81 @@ class LinearPlan:
     def supports(weight):
         return weight.is_cuda and weight.dtype == torch.float32 and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0
 
-    def forward(self, x, gelu=False):
-        """x [..., in_features] fp32 CUDA -> [..., out_features]."""
+    def forward(self, x, gelu=False, residual=None):
+        """x [..., in_features] fp32 CUDA -> [..., out_features] (+ residual of that shape, added in the epilogue)."""
         x = _f32c(x, "x")
         k, n = self.desc.in_features, self.desc.out_features
         if x.shape[-1] != k:
             raise ValueError(f"linear expects {k} input features, got {x.shape[-1]}")
         rows = x.numel() // k
         out = torch.empty(*x.shape[:-1], n, dtype=torch.float32, device=x.device)
+        if residual is not None:
+            residual = _f32c(residual, "residual")
+            if residual.shape != out.shape:
+                raise ValueError(f"residual {tuple(residual.shape)} does not match the output {tuple(out.shape)}")
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().ciaosr_linear_forward(ctypes.byref(self.desc), _ptr(self.buf), _ptr(x), rows,
-                                                         1 if gelu else 0, _ptr(out), _stream(self.device)))
+            _lib.check(_lib.load().ciaosr_linear_forward_res(ctypes.byref(self.desc), _ptr(self.buf), _ptr(x), rows,
+                                                             1 if gelu else 0, _ptr(residual), _ptr(out),
+                                                             _stream(self.device)))
+        return out
+
+
+def conv3x3_plan_for(conv):
+    """The cached Conv3x3Plan of an nn.Conv2d (rebuilt when its parameters change or move), or None when the native
+    path does not support the layer."""
+    if not Conv3x3Plan.supports(conv):
+        return None
+    w = conv.weight
+    key = (w.data_ptr(), w._version, None if conv.bias is None else (conv.bias.data_ptr(), conv.bias._version))
+    mc = module_cache(conv)
+    cache = mc.get("conv_plan")
+    if cache is None or cache[0] != key:
+        cache = mc["conv_plan"] = (key, Conv3x3Plan(w, conv.bias))
+    return cache[1]
+
+
+class Conv3x3Plan:
+    """One nn.Conv2d(Cin, Cout, 3, 1, 1) packed for ``ciaosr_conv3x3_nhwc_forward`` (implicit GEMM on the tensor
+    cores over NHWC maps = token tensors; the SwinIR trunk's RSTB / after-body convolutions)."""
+
+    def __init__(self, weight, bias):
+        lib = _lib.load()
+        self.weight = _f32c(weight.detach(), "weight")
+        self.bias = _f32c(bias.detach(), "bias") if bias is not None else None
+        self.device = self.weight.device
+        d = _lib.Conv3x3Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.out_channels, d.in_channels = self.weight.shape[:2]
+        d.weight = self.weight.data_ptr()
+        d.bias = self.bias.data_ptr() if self.bias is not None else None
+        self.desc = d
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.ciaosr_conv3x3_plan_bytes(ctypes.byref(d), ctypes.byref(n)))
+        with torch.cuda.device(self.device):
+            self.buf = torch.empty(max(n.value, 256), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.ciaosr_conv3x3_plan_init(ctypes.byref(d), _ptr(self.buf), n.value, _stream(self.device)))
+
+    @staticmethod
+    def supports(conv):
+        w = conv.weight
+        return (isinstance(conv, torch.nn.Conv2d) and w.is_cuda and w.dtype == torch.float32
+                and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)
+                and tuple(conv.dilation) == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+                and w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0)
+
+    def forward(self, x, residual=None, relu=False):
+        """x [B, H, W, Cin] (NHWC) -> [B, H, W, Cout]: act(conv(x) + bias) (+ residual)."""
+        x = _f32c(x, "x")
+        b, h, w, c = x.shape
+        if c != self.desc.in_channels:
+            raise ValueError(f"conv expects {self.desc.in_channels} input channels, got {c}")
+        out = torch.empty(b, h, w, self.desc.out_channels, dtype=torch.float32, device=x.device)
+        if residual is not None:
+            residual = _f32c(residual, "residual")
+            if residual.numel() != out.numel():
+                raise ValueError("residual does not match the output")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().ciaosr_conv3x3_nhwc_forward(ctypes.byref(self.desc), _ptr(self.buf), _ptr(x), b, h,
+                                                               w, 2 if relu else 0, _ptr(residual), _ptr(out),
+                                                               _stream(self.device)))
         return out

@@ -51,8 +51,29 @@ class native_linear:
         _NATIVE = self.prev
 
 
-def _linear(x, lin, gelu=False):
-    """`lin(x)` (optionally followed by the exact GELU) for an nn.Linear."""
+def _norm(x, ln):
+    """`ln(x)` for an affine nn.LayerNorm over the last dimension."""
+    if (_NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and ln.elementwise_affine
+            and len(ln.normalized_shape) == 1 and ln.normalized_shape[0] <= 512):
+        from . import native
+        return native.layernorm(x, ln)
+    return ln(x)
+
+
+def _conv3x3_tokens(tokens, x_size, conv, residual=None):
+    """`conv` (an nn.Conv2d 3x3, stride 1, pad 1) applied to a token tensor [B, HW, C] seen as the NHWC map it is,
+    + residual tokens; returns tokens, or None when the native path does not apply."""
+    if _NATIVE and tokens.is_cuda and tokens.dtype == torch.float32 and not torch.is_grad_enabled():
+        from . import native
+        plan = native.conv3x3_plan_for(conv)
+        if plan is not None:
+            b, n, c = tokens.shape
+            return plan.forward(tokens.view(b, x_size[0], x_size[1], c), residual=residual).view(b, n, -1)
+    return None
+
+
+def _linear(x, lin, gelu=False, residual=None):
+    """`lin(x)` (optionally followed by the exact GELU, optionally + residual) for an nn.Linear."""
     w = lin.weight
     if _NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
         from . import native
@@ -62,9 +83,10 @@ def _linear(x, lin, gelu=False):
             cache = mc.get("linear_plan")
             if cache is None or cache[0] != key:
                 cache = mc["linear_plan"] = (key, native.LinearPlan(w, lin.bias))
-            return cache[1].forward(x, gelu=gelu)
+            return cache[1].forward(x, gelu=gelu, residual=residual)
     y = lin(x)
-    return F.gelu(y) if gelu else y
+    y = F.gelu(y) if gelu else y
+    return y if residual is None else residual + y
 
 
 class DropPath(nn.Module):
@@ -197,6 +219,20 @@ class SwinTransformerBlock(nn.Module):
         h, w = x_size
         b, _, c = x.shape
         ws, sh = self.window_size, self.shift_size
+        if _NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
+            from . import native
+            a = self.attn
+            if native.window_attention_supported(c, a.num_heads, ws) and native.LinearPlan.supports(a.qkv.weight):
+                # Encoder fast path: the qkv Linear runs on the tokens in natural order and ONE native kernel does
+                # shift + window partition + bias + mask + attention + reverse (csrc/swin_attn.cu) instead of the
+                # rolls / permutes / expanded mask tensors below; same arithmetic in fp32.
+                o = native.window_attention(_linear(_norm(x, self.norm1), a.qkv), a.relative_position_bias_table,
+                                            h, w, a.num_heads, ws, sh, a.scale)
+                x = _linear(o, a.proj, residual=x)                       # x + proj(o), added in the epilogue
+                m = self.mlp
+                if isinstance(m.act, nn.GELU) and getattr(m.act, "approximate", "none") == "none":
+                    return _linear(_linear(_norm(x, self.norm2), m.fc1, gelu=True), m.fc2, residual=x)
+                return x + m(_norm(x, self.norm2))
         y = self.norm1(x).view(b, h, w, c)
         if sh > 0:
             y = torch.roll(y, shifts=(-sh, -sh), dims=(1, 2))
@@ -244,7 +280,7 @@ class PatchEmbed(nn.Module):
 
     def forward(self, x):
         x = x.flatten(2).transpose(1, 2)
-        return self.norm(x) if self.norm is not None else x
+        return _norm(x, self.norm) if self.norm is not None else x
 
 
 class PatchUnEmbed(nn.Module):
@@ -286,7 +322,12 @@ class RSTB(nn.Module):
         self.patch_unembed = PatchUnEmbed(img_size, patch_size, 0, dim, None)
 
     def forward(self, x, x_size):
-        y = self.patch_unembed(self.residual_group(x, x_size), x_size)
+        t = self.residual_group(x, x_size)
+        if isinstance(self.conv, nn.Conv2d):
+            y = _conv3x3_tokens(t, x_size, self.conv, residual=x)     # tokens are an NHWC map: no (un)embed transposes
+            if y is not None:
+                return y
+        y = self.patch_unembed(t, x_size)
         return self.patch_embed(self.conv(y)) + x
 
 

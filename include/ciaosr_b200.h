@@ -202,7 +202,7 @@ int ciaosr_rdn_forward(const ciaosr_rdn_desc* desc, const void* plan, const floa
  * layers of the SwinIR trunk (qkv / proj / fc1 / fc2, swinir_net.py:15-31, 66-146) that
  * LocalImplicitSRSWINIR.gen_feature runs (ciaosr_net.py:475-525).  weight [out, in]
  * row-major fp32 as in the state_dict, bias [out] or NULL; in/out multiples of 4.
- * activation: 0 none, 1 exact GELU (nn.GELU()).  Same fp16 hi/lo split arithmetic as the
+ * activation: 0 none, 1 exact GELU (nn.GELU()), 2 ReLU (ciaosr_linear_forward_res only).  Same fp16 hi/lo split arithmetic as the
  * head (fp32-grade; TF32 would put the features ~1e-3 off). */
 typedef struct ciaosr_linear_desc {
   int32_t abi_version;
@@ -215,6 +215,47 @@ int ciaosr_linear_plan_bytes(const ciaosr_linear_desc* desc, size_t* bytes);
 int ciaosr_linear_plan_init(const ciaosr_linear_desc* desc, void* plan, size_t plan_bytes, void* stream);
 int ciaosr_linear_forward(const ciaosr_linear_desc* desc, const void* plan, const float* x, long long rows,
                           int activation, float* out, void* stream);
+
+/* as above, plus `residual` [rows, out_features] (or NULL) added after the activation: x + proj(o), x + fc2(h)
+ * of SwinTransformerBlock.forward (swinir_net.py:276-278) without a separate elementwise pass. */
+int ciaosr_linear_forward_res(const ciaosr_linear_desc* desc, const void* plan, const float* x, long long rows,
+                              int activation, const float* residual, float* out, void* stream);
+
+/* ---- fp32-grade 3x3 convolution on NHWC maps (SURVEY.md 8f "next" #2) -------------------------------
+ * nn.Conv2d(Cin, Cout, 3, 1, 1) as the SwinIR trunk uses it after every residual Swin block group and after the body
+ * (`RSTB.conv`, `conv_after_body`; swinir_net.py:446-483, 706-713 -> ciaosr_net.py:503-525), evaluated directly on
+ * the token tensor [B, H*W, C] = NHWC map (no patch_unembed / patch_embed transposes) as an implicit GEMM on the
+ * tensor cores with the same fp16 hi/lo split arithmetic; `residual` [B,H,W,Cout] (or NULL) is added in the epilogue
+ * (the RSTB's `+ x`).  weight [Cout, Cin, 3, 3] row-major as in the state_dict; Cin, Cout multiples of 4. */
+typedef struct ciaosr_conv3x3_desc {
+  int32_t abi_version;
+  int32_t in_channels, out_channels;
+  const float* weight;
+  const float* bias;                       /* [Cout] or NULL */
+} ciaosr_conv3x3_desc;
+
+int ciaosr_conv3x3_plan_bytes(const ciaosr_conv3x3_desc* desc, size_t* bytes);
+int ciaosr_conv3x3_plan_init(const ciaosr_conv3x3_desc* desc, void* plan, size_t plan_bytes, void* stream);
+/* activation: 0 none, 2 ReLU (EDSR's residual blocks); out = act(conv(x) + bias) + residual */
+int ciaosr_conv3x3_nhwc_forward(const ciaosr_conv3x3_desc* desc, const void* plan, const float* x, int B, int H,
+                                int W, int activation, const float* residual, float* out, void* stream);
+
+/* ---- window attention of the SwinIR trunk (SURVEY.md 8f "next" #2) ---------------------------------
+ * W-MSA / SW-MSA as SwinTransformerBlock.forward runs it (swinir_net.py:240-280 around WindowAttention.forward
+ * :112-146): cyclic shift by -shift, ws x ws window partition, per window and head
+ * softmax(q * scale . k^T + relative_position_bias [+ the -100 region mask of SW-MSA when shift > 0]) . v,
+ * window reverse, reverse shift, heads concatenated.
+ * qkv        [B, H*W, 3C]  output of the block's qkv Linear on the LayerNorm'd tokens in natural (y, x) order
+ *                          (q | k | v, each [heads, C/heads])
+ * bias_table [(2ws-1)^2, heads]  relative_position_bias_table as in the state_dict
+ * out        [B, H*W, C]   natural token order: what the block feeds to `proj`
+ * H, W multiples of ws; C/heads <= 32; ws*ws*heads <= 384; 0 <= shift < ws.  fp32 CUDA cores. */
+int ciaosr_window_attention_forward(const float* qkv, const float* bias_table, int B, int H, int W, int C,
+                                    int heads, int ws, int shift, float scale, float* out, void* stream);
+
+/* nn.LayerNorm(C) of the trunk (swinir_net.py:195, 207, 702) over [rows, C] fp32, C <= 512, affine. */
+int ciaosr_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows,
+                             int C, float* out, void* stream);
 
 /* ---- tiled inference epilogue (ciaosr.py:218-258, 160-163) -------------- */
 /* acc/cnt [B,3,Ho,Wo] += tile prediction [B, th*tw, 3] placed at (y0,x0).   */

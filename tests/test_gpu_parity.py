@@ -640,3 +640,111 @@ def test_graph_replay_after_larger_shape_and_weight_update():
     g2 = copy.deepcopy(g)
     with torch.no_grad():
         assert max_abs(g2(*a_in, test_mode=True), a2_eager) == 0.0
+
+
+# ---- native pieces of the SwinIR trunk (encoder fast path) ----------------------------------------
+def _window_attention_reference(qkv, table, h, w, heads, ws, shift, scale):
+    """SwinTransformerBlock's attention path restated with plain tensor ops in float64: roll, partition, per-head
+    softmax(q*scale @ k^T + bias + mask) @ v, reverse, un-roll (swinir_net.py:112-146, 240-280)."""
+    from ciaosr_b200.swinir import relative_position_index, shifted_window_mask
+    b, n, c3 = qkv.shape
+    c, d = c3 // 3, c3 // 3 // heads
+    x = qkv.double().view(b, h, w, c3)
+    if shift:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    win = x.view(b, h // ws, ws, w // ws, ws, c3).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, c3)
+    q, k, v = win.view(-1, ws * ws, 3, heads, d).permute(2, 0, 3, 1, 4)
+    attn = (q * scale) @ k.transpose(-2, -1)
+    bias = table.double()[relative_position_index((ws, ws)).reshape(-1).to(table.device)].view(ws * ws, ws * ws, heads)
+    attn = attn + bias.permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        mask = shifted_window_mask((h, w), ws, shift).double().to(qkv.device)
+        nw = mask.shape[0]
+        attn = (attn.view(-1, nw, heads, ws * ws, ws * ws) + mask.view(1, nw, 1, ws * ws, ws * ws)).view(-1, heads, ws * ws, ws * ws)
+    out = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, ws * ws, c)
+    out = out.view(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+    if shift:
+        out = torch.roll(out, shifts=(shift, shift), dims=(1, 2))
+    return out.reshape(b, n, c)
+
+
+@pytest.mark.parametrize("c,heads,ws,h,w,b", [(180, 6, 8, 24, 40, 2), (24, 2, 4, 8, 12, 1), (180, 6, 8, 8, 8, 1)])
+def test_native_window_attention(c, heads, ws, h, w, b):
+    from ciaosr_b200 import native
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(b, h * w, 3 * c, generator=g).to(dev)
+    table = (torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5).to(dev)
+    scale = (c // heads) ** -0.5
+    for shift in (0, ws // 2):
+        if shift and min(h, w) <= ws:
+            continue
+        out = native.window_attention(qkv, table, h, w, heads, ws, shift, scale)
+        ref = _window_attention_reference(qkv, table, h, w, heads, ws, shift, scale)
+        assert max_abs(out, ref) < 5e-6, (shift, max_abs(out, ref))
+
+
+def test_native_layernorm_conv3x3_and_fused_residuals():
+    from ciaosr_b200 import native
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    # LayerNorm
+    for rows, c in [(1000, 180), (37, 24), (5, 512)]:
+        ln = torch.nn.LayerNorm(c).to(dev)
+        with torch.no_grad():
+            ln.weight.copy_(1 + 0.1 * torch.randn(c, generator=g))
+            ln.bias.copy_(0.1 * torch.randn(c, generator=g))
+        x = (torch.randn(rows, c, generator=g) * 3 + 1).to(dev)
+        ref = torch.nn.functional.layer_norm(x.double(), (c,), ln.weight.double(), ln.bias.double(), ln.eps)
+        assert max_abs(native.layernorm(x, ln), ref) < 3e-6
+    # 3x3 convolution on NHWC tokens + residual
+    for b, h, w, cin, cout in [(2, 19, 21, 180, 180), (1, 8, 8, 24, 24), (1, 33, 5, 64, 12)]:
+        conv = torch.nn.Conv2d(cin, cout, 3, 1, 1).to(dev)
+        x = torch.randn(b, h, w, cin, generator=g).to(dev)
+        res = torch.randn(b, h, w, cout, generator=g).to(dev)
+        plan = native.Conv3x3Plan(conv.weight, conv.bias)
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), conv.bias.double(),
+                                         padding=1).permute(0, 2, 3, 1)
+        assert max_abs(plan.forward(x), ref) < 2e-5
+        assert max_abs(plan.forward(x, residual=res), ref + res.double()) < 2e-5
+    # Linear with fused residual; short K with several N-chunks runs in the A-resident mode
+    for rows, k, n in [(700, 180, 540), (129, 180, 360), (64, 360, 180), (300, 24, 72)]:
+        x = torch.randn(rows, k, generator=g).to(dev)
+        wgt = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev)
+        bias = (0.1 * torch.randn(n, generator=g)).to(dev)
+        res = torch.randn(rows, n, generator=g).to(dev)
+        plan = native.LinearPlan(wgt, bias)
+        ref = x.double() @ wgt.double().t() + bias.double()
+        assert max_abs(plan.forward(x), ref) < 2e-5
+        assert max_abs(plan.forward(x, residual=res), ref + res.double()) < 2e-5
+        assert max_abs(plan.forward(x, gelu=True, residual=res), torch.nn.functional.gelu(ref) + res.double()) < 2e-5
+
+
+def test_native_edsr_encoder_matches_pytorch():
+    """Encoder fast path of LocalImplicitSREDSR (BASELINE.json config 1's encoder: EDSR-baseline 16 blocks x 64):
+    tensor-core implicit-GEMM trunk vs the PyTorch fp32 trunk (cuDNN, TF32 off), and through the whole generator."""
+    from ciaosr_b200.builder import build
+    dev = _dev()
+    from tests.util import generator_cfg
+    g = build(generator_cfg(64, [256, 256, 256, 256], 30000, num_blocks=16))
+    synth.fill_module(g, 19)
+    g = g.eval().to(dev)
+    for b, h, w in [(1, 48, 48), (2, 17, 23)]:
+        x = synth.synth_lr_image(b, h, w, 19).to(dev)
+        with torch.no_grad():
+            g.native_encoder = False
+            ref = g.gen_feature(x)[0]
+            g.native_encoder = True
+            out = g.gen_feature(x)[0]
+        assert out.shape == ref.shape == (b, 64, h, w)
+        scale = float(ref.abs().max())
+        err = max_abs(out, ref)
+        print(f"EDSR native encoder {b}x{h}x{w}: feature max-abs {err:.2e} (|feature| max {scale:.2f}, 34 convolutions deep)")
+        # 34 chained fp32-grade convolutions (each ~1e-6 relative to the running magnitude, like cuDNN fp32 vs fp64)
+        assert 0.0 < err < 2e-5 * max(1.0, scale), (err, scale)
+        k = 0.5 / float(ref.std())
+        coord = make_coord((h * 2, w * 2)).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        cell = make_cell((h * 2, w * 2), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous().to(dev)
+        y0 = g.query_rgb([(ref * k).contiguous()], coord, cell)
+        y1 = g.query_rgb([(out * k).contiguous()], coord, cell)
+        assert max_abs(y0, y1) < TOL
