@@ -35,6 +35,7 @@ EXPORTS = (
     "ciaosr_linear_plan_bytes", "ciaosr_linear_plan_init", "ciaosr_linear_forward",
     "ciaosr_window_attention_forward", "ciaosr_layernorm_forward", "ciaosr_linear_forward_res",
     "ciaosr_conv3x3_plan_bytes", "ciaosr_conv3x3_plan_init", "ciaosr_conv3x3_nhwc_forward",
+    "ciaosr_linear_forward_split", "ciaosr_layernorm_split_forward", "ciaosr_window_attention_split_forward",
 )
 
 
@@ -149,6 +150,12 @@ def load():
     lib.ciaosr_conv3x3_plan_init.argtypes = [POINTER(Conv3x3Desc), c_void_p, c_size_t, c_void_p]
     lib.ciaosr_conv3x3_nhwc_forward.argtypes = [POINTER(Conv3x3Desc), c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                 c_void_p, c_void_p, c_void_p]
+    lib.ciaosr_linear_forward_split.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_void_p, c_int, c_longlong,
+                                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.ciaosr_layernorm_split_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_longlong, c_int, c_void_p,
+                                                   c_void_p, c_int, c_void_p]
+    lib.ciaosr_window_attention_split_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                          c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]
     lib.ciaosr_layernorm_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_longlong, c_int, c_void_p,
                                              c_void_p]
     for name in EXPORTS[3:]:  # everything after the three non-int getters

@@ -74,6 +74,16 @@ struct TmaRowsGen {          // the generic "A comes through the tensor maps" ge
   __device__ __forceinline__ void fill(Row&, long long, int, float (&)[32]) const {}
 };
 
+// AGen::kPrefetch = true: fill() is split into  issue(Row&, m, k0, Raw&)  -- address arithmetic + the 8 float4 loads of
+// a 32-column chunk, nothing that waits on them -- and  finish(Row&, m, k0, const Raw&, v)  -- masking / arithmetic on the
+// loaded values.  The row threads then issue slab s+1's loads BEFORE converting and storing slab s, so the L2 / HBM
+// latency of a gather overlaps the split + st.shared + fence of the previous slab instead of being exposed once per slab
+// (ncu r02f: the short-K Linear kernels spent most of their time in long-scoreboard stalls on exactly these loads).
+template <class AGen, class = void>
+struct agen_prefetch : std::false_type {};
+template <class AGen>
+struct agen_prefetch<AGen, std::enable_if_t<AGen::kPrefetch>> : std::true_type {};
+
 template <class Epi, class Row, class = void>
 struct epi_accumulates : std::false_type {};
 template <class Epi, class Row>
@@ -162,19 +172,48 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
         for (int kc = 0; kc < n_kc; ++kc) {
           const int sl_end = k0 + min((kc + 1) * kchunk, klen);
           if (!resident || nc == 0) {
-#pragma unroll 1
-            for (int sl = k0 + kc * kchunk; sl < sl_end; ++sl) {
-              const int slot = (sl - k0) & 3;
-              if constexpr (agen_tma<AGen>::value) { e.afree_bits ^= 1u << slot; continue; }   // producer-loaded slab
-              float v[32];
-              if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
-              else {
+            if constexpr (agen_prefetch<AGen>::value) {
+              // software-pipelined: the loads of slab sl+1 are in flight while slab sl is converted and stored.
+              // Two named buffers used alternately (a runtime-indexed array would live in local memory).
+              typename AGen::Raw ra, rb;
+              const int sl0 = k0 + kc * kchunk;
+              auto process = [&](int sl, const typename AGen::Raw& raw) {
+                const int slot = (sl - k0) & 3;
+                float v[32];
+                if (valid) agen.finish(rs, m, sl * 64 + half * 32, raw, v);
+                else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                }
+                slab_begin(s, e, slot, true);
+                a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+                slab_done(s, slot);
+              };
+              if (valid && sl0 < sl_end) agen.issue(rs, m, sl0 * 64 + half * 32, ra);
+#pragma unroll 1
+              for (int sl = sl0; sl < sl_end; sl += 2) {
+                if (valid && sl + 1 < sl_end) agen.issue(rs, m, (sl + 1) * 64 + half * 32, rb);
+                process(sl, ra);
+                if (sl + 1 < sl_end) {
+                  if (valid && sl + 2 < sl_end) agen.issue(rs, m, (sl + 2) * 64 + half * 32, ra);
+                  process(sl + 1, rb);
+                }
               }
-              slab_begin(s, e, slot, true);
-              a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
-              slab_done(s, slot);
+            } else {
+#pragma unroll 1
+              for (int sl = k0 + kc * kchunk; sl < sl_end; ++sl) {
+                const int slot = (sl - k0) & 3;
+                if constexpr (agen_tma<AGen>::value) { e.afree_bits ^= 1u << slot; continue; }   // producer-loaded slab
+                float v[32];
+                if (valid) agen.fill(rs, m, sl * 64 + half * 32, v);
+                else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                }
+                slab_begin(s, e, slot, true);
+                a_store32(s.a_hi + slot * SLAB_BYTES, s.a_lo + slot * SLAB_BYTES, row, half * 32, v);
+                slab_done(s, slot);
+              }
             }
           }
           if constexpr (agen_combines<AGen>::value) {

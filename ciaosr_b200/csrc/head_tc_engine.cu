@@ -177,37 +177,43 @@ int tc_pack(const ciaosr_head_desc* d, const PlanLayout& L, float* plan, cudaStr
 // unconditional (out-of-image taps read the row's own pixel and are masked afterwards), so the 8 (or 16)
 // loads of a chunk are in flight together instead of one L2 round trip per branch.
 struct UnfoldGen {       // A[pix, kp] = tap-major 3x3 unfold of the NHWC feature (+ non-local channels)
+  static constexpr bool kPrefetch = true;     // loads of the next slab overlap the split / store of this one (gemm_tc.cuh)
   const float* f; const float* nl; int H, W, C, Cn, K;
   struct Row { int y, x; };
+  struct Raw { float4 q[8]; uint32_t ok; };
   __device__ __forceinline__ Row row(long long m) const {
     const int hw = (int)(m % ((long long)H * W));
     return Row{hw / W, hw % W};
   }
-  __device__ __forceinline__ void fill(Row& r, long long m, int k0, float (&v)[32]) const {
+  __device__ __forceinline__ void issue(Row& r, long long m, int k0, Raw& w) const {
     const float* src[8];
-    bool ok[8];
     const float* self = f + m * C;
+    w.ok = 0;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      src[g] = self; ok[g] = false;
+      src[g] = self;
       if (k < 9 * C) {
         const int t = k / C, ch = k - t * C;
         const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
-        ok[g] = r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W;
-        if (ok[g]) src[g] = self + (dy * W + dx) * C + ch;
+        if (r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W) {
+          src[g] = self + (dy * W + dx) * C + ch;
+          w.ok |= 1u << g;
+        }
       } else if (k < K) {
-        ok[g] = true;
+        w.ok |= 1u << g;
         src[g] = nl + m * Cn + (k - 9 * C);
       }
     }
-    float4 q[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+    for (int g = 0; g < 8; ++g) w.q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+  }
+  __device__ __forceinline__ void finish(Row&, long long, int, const Raw& w, float (&v)[32]) const {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
-      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
+      const bool ok = (w.ok >> g) & 1;
+      v[4 * g] = ok ? w.q[g].x : 0.f; v[4 * g + 1] = ok ? w.q[g].y : 0.f;
+      v[4 * g + 2] = ok ? w.q[g].z : 0.f; v[4 * g + 3] = ok ? w.q[g].w : 0.f;
     }
   }
 };

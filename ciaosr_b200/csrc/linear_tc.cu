@@ -11,21 +11,24 @@
 namespace ciaosr {
 
 struct LinRowsGen {        // A = fp32 rows [M, K], K % 4 == 0; columns past K read as zero
+  static constexpr bool kPrefetch = true;
   const float* x; int K;
   struct Row { const float* r; };
+  struct Raw { float4 q[8]; };
   __device__ __forceinline__ Row row(long long m) const { return Row{x + m * K}; }
-  __device__ __forceinline__ void fill(Row& r, long long, int k0, float (&v)[32]) const {
-    float4 q[8];
+  __device__ __forceinline__ void issue(Row& r, long long, int k0, Raw& w) const {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      q[g] = __ldg(reinterpret_cast<const float4*>(r.r + (k < K ? k : 0)));
+      w.q[g] = __ldg(reinterpret_cast<const float4*>(r.r + (k < K ? k : 0)));
     }
+  }
+  __device__ __forceinline__ void finish(Row&, long long, int k0, const Raw& w, float (&v)[32]) const {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const bool ok = k0 + 4 * g < K;
-      v[4 * g] = ok ? q[g].x : 0.f; v[4 * g + 1] = ok ? q[g].y : 0.f;
-      v[4 * g + 2] = ok ? q[g].z : 0.f; v[4 * g + 3] = ok ? q[g].w : 0.f;
+      v[4 * g] = ok ? w.q[g].x : 0.f; v[4 * g + 1] = ok ? w.q[g].y : 0.f;
+      v[4 * g + 2] = ok ? w.q[g].z : 0.f; v[4 * g + 3] = ok ? w.q[g].w : 0.f;
     }
   }
 };
@@ -33,26 +36,54 @@ struct LinSrc {            // B[n, k] = W[n, k]
   const float* w; int K;
   __device__ __forceinline__ float operator()(int, int n, int k) const { return w[(long long)n * K + k]; }
 };
-struct LinEpi {            // out[m, n] = act(acc + bias[n]) (+ res[m, n]), N % 4 == 0
+// out[m, n] = act(acc + bias[n]) (+ res[m, n]), N % 4 == 0; bias 16-byte aligned.  o != nullptr: fp32 rows [M, N];
+// else the fp16 hi / lo halves [M, ldo] (ldo % 8 == 0, pad columns zeroed) that the next TMA-fed Linear reads.
+struct LinEpi {
   float* o; const float* bias; int N; int act; const float* res;
+  split_t* o_hi = nullptr; split_t* o_lo = nullptr; int ldo = 0;
   template <class Row>
   __device__ __forceinline__ void store(const Row&, long long m, int n0, const float (&v)[32]) const {
     float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
     const float4* rsrc = res ? reinterpret_cast<const float4*>(res + m * N + n0) : nullptr;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + 4 * j;
-      if (n >= N) break;
-      float t[4];
+    for (int hh = 0; hh < 2; ++hh) {                  // two halves of 16 columns: the 8 loads of a half are issued together
+      float4 b4[4], r4[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a = v[4 * j + i] + (bias ? __ldg(bias + n + i) : 0.0f);
-        if (act == 1) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));      // nn.GELU() (exact)
-        else if (act == 2) a = fmaxf(a, 0.0f);                                         // nn.ReLU()
-        t[i] = a;
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * hh + jj;
+        const bool in = n0 + 4 * j < N;
+        b4[jj] = (bias && in) ? __ldg(reinterpret_cast<const float4*>(bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r4[jj] = (rsrc && in) ? __ldg(rsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (rsrc) { const float4 r = __ldg(rsrc + j); t[0] += r.x; t[1] += r.y; t[2] += r.z; t[3] += r.w; }
-      dst[j] = make_float4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * hh + jj;
+        if (n0 + 4 * j >= N) break;
+        const float bb[4] = {b4[jj].x, b4[jj].y, b4[jj].z, b4[jj].w};
+        float t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = v[4 * j + i] + bb[i];
+          if (act == 1) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));      // nn.GELU() (exact)
+          else if (act == 2) a = fmaxf(a, 0.0f);                                         // nn.ReLU()
+          t[i] = a;
+        }
+        t[0] += r4[jj].x; t[1] += r4[jj].y; t[2] += r4[jj].z; t[3] += r4[jj].w;
+        if (o != nullptr) dst[j] = make_float4(t[0], t[1], t[2], t[3]);
+        else {
+          uint2 h, l;
+          split2(t[0], t[1], h.x, l.x);
+          split2(t[2], t[3], h.y, l.y);
+          *reinterpret_cast<uint2*>(o_hi + m * ldo + n0 + 4 * j) = h;
+          *reinterpret_cast<uint2*>(o_lo + m * ldo + n0 + 4 * j) = l;
+        }
+      }
+    }
+    if (o == nullptr && n0 <= N && N < n0 + 32 && N < ldo) {          // the chunk that holds column N: zero the pad
+      for (int c = N; c < ldo; c += 4) {
+        *reinterpret_cast<uint2*>(o_hi + m * ldo + c) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(o_lo + m * ldo + c) = make_uint2(0u, 0u);
+      }
     }
   }
 };
@@ -62,34 +93,40 @@ struct LinEpi {            // out[m, n] = act(acc + bias[n]) (+ res[m, n]), N % 
 // The RSTB / trunk convolutions of SwinIR (swinir_net.py:446-483, 706-713) act on token tensors [B, HW, C], which ARE
 // NHWC maps: no patch_unembed / patch_embed transposes, and the RSTB's residual rides in the epilogue.
 struct Conv3Gen {
+  static constexpr bool kPrefetch = true;
   const float* x; int H, W, C;
   struct Row { int y, x; };
+  struct Raw { float4 q[8]; uint32_t ok; };
   __device__ __forceinline__ Row row(long long m) const {
     const int hw = (int)(m % ((long long)H * W));
     return Row{hw / W, hw % W};
   }
-  __device__ __forceinline__ void fill(Row& r, long long m, int k0, float (&v)[32]) const {
+  __device__ __forceinline__ void issue(Row& r, long long m, int k0, Raw& w) const {
     const float* src[8];
-    bool ok[8];
     const float* self = x + m * C;
+    w.ok = 0;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int k = k0 + 4 * g;
-      src[g] = self; ok[g] = false;
+      src[g] = self;
       if (k < 9 * C) {
         const int t = k / C, ch = k - t * C;
         const int dy = t / 3 - 1, dx = t - (dy + 1) * 3 - 1;
-        ok[g] = r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W;
-        if (ok[g]) src[g] = self + (dy * W + dx) * C + ch;
+        if (r.y + dy >= 0 && r.y + dy < H && r.x + dx >= 0 && r.x + dx < W) {
+          src[g] = self + (dy * W + dx) * C + ch;
+          w.ok |= 1u << g;
+        }
       }
     }
-    float4 q[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+    for (int g = 0; g < 8; ++g) w.q[g] = __ldg(reinterpret_cast<const float4*>(src[g]));
+  }
+  __device__ __forceinline__ void finish(Row&, long long, int, const Raw& w, float (&v)[32]) const {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      v[4 * g] = ok[g] ? q[g].x : 0.f; v[4 * g + 1] = ok[g] ? q[g].y : 0.f;
-      v[4 * g + 2] = ok[g] ? q[g].z : 0.f; v[4 * g + 3] = ok[g] ? q[g].w : 0.f;
+      const bool ok = (w.ok >> g) & 1;
+      v[4 * g] = ok ? w.q[g].x : 0.f; v[4 * g + 1] = ok ? w.q[g].y : 0.f;
+      v[4 * g + 2] = ok ? w.q[g].z : 0.f; v[4 * g + 3] = ok ? w.q[g].w : 0.f;
     }
   }
 };
@@ -108,6 +145,7 @@ static int lin_check(const ciaosr_linear_desc* d) {
                  CIAOSR_E_INVALID, "linear: in_features and out_features must be positive multiples of 4, got %d -> %d",
                  d->in_features, d->out_features);
   CIAOSR_REQUIRE(d->weight != nullptr, CIAOSR_E_INVALID, "linear: weight is NULL");
+  CIAOSR_REQUIRE(((uintptr_t)d->bias % 16) == 0, CIAOSR_E_INVALID, "linear: bias must be 16-byte aligned");
   return CIAOSR_OK;
 }
 
@@ -163,6 +201,31 @@ int ciaosr_linear_forward_res(const ciaosr_linear_desc* d, const void* plan, con
                  LinEpi{out, d->bias, d->out_features, activation, residual}, (cudaStream_t)stream);
 }
 
+int ciaosr_linear_forward_split(const ciaosr_linear_desc* d, const void* plan, const uint16_t* a_hi,
+                                const uint16_t* a_lo, int lda, long long rows, int activation, const float* residual,
+                                float* out, uint16_t* out_hi, uint16_t* out_lo, int ldo, void* stream) {
+  int rc = lin_check(d);
+  if (rc) return rc;
+  CIAOSR_REQUIRE(plan && a_hi && a_lo && (out || (out_hi && out_lo)), CIAOSR_E_INVALID, "NULL pointer argument");
+  CIAOSR_REQUIRE(rows >= 0 && activation >= 0 && activation <= 2, CIAOSR_E_INVALID,
+                 "linear: bad rows=%lld or activation=%d", rows, activation);
+  CIAOSR_REQUIRE(lda >= d->in_features && lda % 8 == 0, CIAOSR_E_INVALID,
+                 "linear (split input): lda=%d must be a multiple of 8 >= in_features=%d", lda, d->in_features);
+  CIAOSR_REQUIRE(out || (ldo >= d->out_features && ldo % 8 == 0), CIAOSR_E_INVALID,
+                 "linear (split output): ldo=%d must be a multiple of 8 >= out_features=%d", ldo, d->out_features);
+  if (rows == 0) return CIAOSR_OK;
+  StageScope sc(6, (cudaStream_t)stream);
+  const int kslabs = (d->in_features + KSLAB - 1) / KSLAB, nunits = (d->out_features + UNIT_N - 1) / UNIT_N;
+  // columns [in_features, lda) of the operand matrices are zero by contract, columns past lda read as zero (TMA)
+  CUtensorMap map_hi, map_lo;
+  if ((rc = tma_make_map_2d(&map_hi, const_cast<uint16_t*>(a_hi), rows, lda)) ||
+      (rc = tma_make_map_2d(&map_lo, const_cast<uint16_t*>(a_lo), rows, lda))) return rc;
+  LinEpi epi{out, d->bias, d->out_features, activation, residual};
+  if (out == nullptr) { epi.o_hi = reinterpret_cast<split_t*>(out_hi); epi.o_lo = reinterpret_cast<split_t*>(out_lo); epi.ldo = ldo; }
+  return tc_gemm(GemmShape{rows, kslabs, nunits, rows, 0}, reinterpret_cast<const uint8_t*>(plan), TmaRowsGen{}, epi,
+                 (cudaStream_t)stream, &map_hi, &map_lo);
+}
+
 static int conv_check(const ciaosr_conv3x3_desc* d) {
   CIAOSR_REQUIRE(d != nullptr, CIAOSR_E_INVALID, "desc is NULL");
   CIAOSR_REQUIRE(d->abi_version == CIAOSR_ABI_VERSION, CIAOSR_E_INVALID, "ABI version mismatch");
@@ -170,6 +233,7 @@ static int conv_check(const ciaosr_conv3x3_desc* d) {
                  CIAOSR_E_INVALID, "conv3x3: channel counts must be positive multiples of 4, got %d -> %d",
                  d->in_channels, d->out_channels);
   CIAOSR_REQUIRE(d->weight != nullptr, CIAOSR_E_INVALID, "conv3x3: weight is NULL");
+  CIAOSR_REQUIRE(((uintptr_t)d->bias % 16) == 0, CIAOSR_E_INVALID, "conv3x3: bias must be 16-byte aligned");
   return CIAOSR_OK;
 }
 
@@ -209,3 +273,18 @@ int ciaosr_conv3x3_nhwc_forward(const ciaosr_conv3x3_desc* d, const void* plan, 
 }
 
 }  // extern "C"
+
+#ifdef CIAOSR_TC_TIMING
+// diagnostic build only: cycles spent in mbarrier waits by the kernels of this translation unit (tools/wait_linear.py)
+extern "C" int ciaosr_debug_wait_read_linear(unsigned long long* cycles, unsigned long long* counts, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(cycles, ciaosr::tc::g_wait_cycles, 64 * 8);
+  cudaMemcpyFromSymbol(counts, ciaosr::tc::g_wait_count, 64 * 8);
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_cycles, z, 64 * 8);
+    cudaMemcpyToSymbol(ciaosr::tc::g_wait_count, z, 64 * 8);
+  }
+  return 0;
+}
+#endif

@@ -95,7 +95,7 @@ class LocalImplicitSRNet(nn.Module):
         for m in self.modules():
             for v in native.module_cache(m).values():
                 plan = v[1] if isinstance(v, tuple) and len(v) == 2 else v
-                if isinstance(plan, (native.HeadPlan, native.RdnPlan, native.LinearPlan)):
+                if isinstance(plan, (native.HeadPlan, native.RdnPlan, native.LinearPlan, native.Conv3x3Plan)):
                     keep += [plan, plan.buf, getattr(plan, "_ws", None)]
         return keep
 

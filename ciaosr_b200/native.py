@@ -212,13 +212,42 @@ def tile_blend_finish(acc, cnt, mean=None, std=None, clamp01=False):
     return out
 
 
+class SplitTensor:
+    """A [rows, features] fp32 matrix in the representation the tensor-core kernels compute in: fp16 `hi` and `lo`
+    halves (x = hi + lo), row stride `ld` (multiple of 8), columns [features, ld) zero.  Produced by
+    layernorm_split / window_attention(split_out=True) / LinearPlan.forward_split(split_out=True) and consumed by
+    LinearPlan.forward_split, whose operand tiles are then TMA-loaded instead of re-split from fp32 per GEMM."""
+
+    def __init__(self, rows, features, device):
+        self.rows, self.features, self.ld = rows, features, (features + 7) // 8 * 8
+        self.hi = torch.empty(rows, self.ld, dtype=torch.float16, device=device)
+        self.lo = torch.empty(rows, self.ld, dtype=torch.float16, device=device)
+
+    def float(self):
+        return (self.hi.float() + self.lo.float())[:, :self.features]
+
+
+def layernorm_split(x, ln):
+    """nn.LayerNorm over the last dim -> SplitTensor [x.numel() / C, C] (ciaosr_layernorm_split_forward)."""
+    x = _f32c(x, "x")
+    c = x.shape[-1]
+    out = SplitTensor(x.numel() // c, c, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ciaosr_layernorm_split_forward(
+            _ptr(x), _ptr(_f32c(ln.weight.detach(), "weight")), _ptr(_f32c(ln.bias.detach(), "bias")), float(ln.eps),
+            out.rows, c, _ptr(out.hi), _ptr(out.lo), out.ld, _stream(x.device)))
+    return out
+
+
 def window_attention_supported(c, heads, ws):
-    return heads > 0 and c % heads == 0 and c // heads <= 32 and ws * ws * heads <= 384
+    threads = (ws * ws * heads + 31) // 32 * 32
+    return heads > 0 and c % heads == 0 and c % 4 == 0 and c // heads <= 32 and ws * ws * heads <= 384 \
+        and c // 2 <= threads
 
 
-def window_attention(qkv, bias_table, h, w, heads, ws, shift, scale):
-    """qkv [B, H*W, 3C] (natural token order) -> [B, H*W, C]: shifted-window multi-head attention with relative
-    position bias and SW-MSA mask (ciaosr_window_attention_forward)."""
+def window_attention(qkv, bias_table, h, w, heads, ws, shift, scale, split_out=False):
+    """qkv [B, H*W, 3C] (natural token order) -> [B, H*W, C] (or a SplitTensor [B*H*W, C] with split_out): shifted-window
+    multi-head attention with relative position bias and SW-MSA mask (ciaosr_window_attention_forward)."""
     qkv, bias_table = _f32c(qkv, "qkv"), _f32c(bias_table.detach(), "relative_position_bias_table")
     b, n, c3 = qkv.shape
     if n != h * w or c3 % 3:
@@ -226,6 +255,13 @@ def window_attention(qkv, bias_table, h, w, heads, ws, shift, scale):
     c = c3 // 3
     if tuple(bias_table.shape) != ((2 * ws - 1) ** 2, heads):
         raise ValueError(f"bias table must be [{(2 * ws - 1) ** 2}, {heads}], got {tuple(bias_table.shape)}")
+    if split_out:
+        out = SplitTensor(b * n, c, qkv.device)
+        with torch.cuda.device(qkv.device):
+            _lib.check(_lib.load().ciaosr_window_attention_split_forward(
+                _ptr(qkv), _ptr(bias_table), b, h, w, c, heads, ws, shift, float(scale), _ptr(out.hi), _ptr(out.lo),
+                out.ld, _stream(qkv.device)))
+        return out
     out = torch.empty(b, n, c, dtype=torch.float32, device=qkv.device)
     with torch.cuda.device(qkv.device):
         _lib.check(_lib.load().ciaosr_window_attention_forward(
@@ -353,7 +389,8 @@ class LinearPlan:
     def __init__(self, weight, bias):
         lib = _lib.load()
         self.weight = _f32c(weight.detach(), "weight")
-        self.bias = _f32c(bias.detach(), "bias") if bias is not None else None
+        # a private copy of the bias: the epilogue reads it as float4, so it must be 16-byte aligned
+        self.bias = _f32c(bias.detach(), "bias").clone() if bias is not None else None
         self.device = self.weight.device
         d = _lib.LinearDesc()
         d.abi_version = _lib.ABI_VERSION
@@ -390,6 +427,19 @@ class LinearPlan:
         return out
 
 
+def linear_plan_for(lin):
+    """The cached LinearPlan of an nn.Linear (rebuilt when its parameters change or move), or None if unsupported."""
+    w = lin.weight
+    if not LinearPlan.supports(w):
+        return None
+    key = (w.data_ptr(), w._version, None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+    mc = module_cache(lin)
+    cache = mc.get("linear_plan")
+    if cache is None or cache[0] != key:
+        cache = mc["linear_plan"] = (key, LinearPlan(w, lin.bias))
+    return cache[1]
+
+
 def conv3x3_plan_for(conv):
     """The cached Conv3x3Plan of an nn.Conv2d (rebuilt when its parameters change or move), or None when the native
     path does not support the layer."""
@@ -404,6 +454,33 @@ def conv3x3_plan_for(conv):
     return cache[1]
 
 
+def _linear_forward_split(self, a, gelu=False, residual=None, split_out=False, out_shape=None):
+    """`a` SplitTensor [rows, in_features] -> fp32 [*out_shape or (rows,), out_features] (+ residual), or a SplitTensor
+    with split_out (ciaosr_linear_forward_split: TMA-fed operand, nothing re-split in the GEMM)."""
+    k, n = self.desc.in_features, self.desc.out_features
+    if a.features != k:
+        raise ValueError(f"linear expects {k} input features, got {a.features}")
+    out = out_hi = out_lo = None
+    ldo = 0
+    if split_out:
+        res = SplitTensor(a.rows, n, a.hi.device)
+        out_hi, out_lo, ldo = res.hi, res.lo, res.ld
+    else:
+        res = out = torch.empty(*(out_shape or (a.rows,)), n, dtype=torch.float32, device=a.hi.device)
+    if residual is not None:
+        residual = _f32c(residual, "residual")
+        if residual.numel() != a.rows * n:
+            raise ValueError("residual does not match the output")
+    with torch.cuda.device(self.device):
+        _lib.check(_lib.load().ciaosr_linear_forward_split(
+            ctypes.byref(self.desc), _ptr(self.buf), _ptr(a.hi), _ptr(a.lo), a.ld, a.rows, 1 if gelu else 0,
+            _ptr(residual), _ptr(out), _ptr(out_hi), _ptr(out_lo), ldo, _stream(self.device)))
+    return res
+
+
+LinearPlan.forward_split = _linear_forward_split
+
+
 class Conv3x3Plan:
     """One nn.Conv2d(Cin, Cout, 3, 1, 1) packed for ``ciaosr_conv3x3_nhwc_forward`` (implicit GEMM on the tensor
     cores over NHWC maps = token tensors; the SwinIR trunk's RSTB / after-body convolutions)."""
@@ -411,7 +488,7 @@ class Conv3x3Plan:
     def __init__(self, weight, bias):
         lib = _lib.load()
         self.weight = _f32c(weight.detach(), "weight")
-        self.bias = _f32c(bias.detach(), "bias") if bias is not None else None
+        self.bias = _f32c(bias.detach(), "bias").clone() if bias is not None else None     # float4-aligned copy
         self.device = self.weight.device
         d = _lib.Conv3x3Desc()
         d.abi_version = _lib.ABI_VERSION

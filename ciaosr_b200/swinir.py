@@ -222,17 +222,25 @@ class SwinTransformerBlock(nn.Module):
         if _NATIVE and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
             from . import native
             a = self.attn
-            if native.window_attention_supported(c, a.num_heads, ws) and native.LinearPlan.supports(a.qkv.weight):
-                # Encoder fast path: the qkv Linear runs on the tokens in natural order and ONE native kernel does
-                # shift + window partition + bias + mask + attention + reverse (csrc/swin_attn.cu) instead of the
-                # rolls / permutes / expanded mask tensors below; same arithmetic in fp32.
-                o = native.window_attention(_linear(_norm(x, self.norm1), a.qkv), a.relative_position_bias_table,
-                                            h, w, a.num_heads, ws, sh, a.scale)
-                x = _linear(o, a.proj, residual=x)                       # x + proj(o), added in the epilogue
-                m = self.mlp
-                if isinstance(m.act, nn.GELU) and getattr(m.act, "approximate", "none") == "none":
-                    return _linear(_linear(_norm(x, self.norm2), m.fc1, gelu=True), m.fc2, residual=x)
-                return x + m(_norm(x, self.norm2))
+            m = self.mlp
+            plans = [native.linear_plan_for(l) for l in (a.qkv, a.proj, m.fc1, m.fc2)]
+            exact_gelu = isinstance(m.act, nn.GELU) and getattr(m.act, "approximate", "none") == "none"
+            if (native.window_attention_supported(c, a.num_heads, ws) and all(p is not None for p in plans)
+                    and exact_gelu and (c // a.num_heads) % 2 == 0 and self.norm1.elementwise_affine
+                    and self.norm2.elementwise_affine and c <= 512):
+                # Encoder fast path: the whole block in 7 native kernels.  Activations travel between them in the fp16
+                # hi / lo split form the tensor-core GEMMs compute in (native.SplitTensor): LayerNorm, the attention
+                # kernel and fc1's epilogue WRITE that form, so every Linear's operand tiles are TMA-loaded instead of
+                # being gathered and re-split from fp32 by the GEMM's row threads (the bound of these short-K GEMMs).
+                # The attention kernel reads the qkv Linear's output in natural token order: shift, window partition,
+                # relative position bias, SW-MSA mask and their inverses are index arithmetic (csrc/swin_attn.cu).
+                qkv_p, proj_p, fc1_p, fc2_p = plans
+                qkv = qkv_p.forward_split(native.layernorm_split(x, self.norm1), out_shape=(b, h * w))
+                o = native.window_attention(qkv, a.relative_position_bias_table, h, w, a.num_heads, ws, sh, a.scale,
+                                            split_out=True)
+                x = proj_p.forward_split(o, residual=x, out_shape=(b, h * w))          # x + proj(o)
+                g = fc1_p.forward_split(native.layernorm_split(x, self.norm2), gelu=True, split_out=True)
+                return fc2_p.forward_split(g, residual=x, out_shape=(b, h * w))        # x + fc2(gelu(fc1(.)))
         y = self.norm1(x).view(b, h, w, c)
         if sh > 0:
             y = torch.roll(y, shifts=(-sh, -sh), dims=(1, 2))

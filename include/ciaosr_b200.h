@@ -221,6 +221,18 @@ int ciaosr_linear_forward(const ciaosr_linear_desc* desc, const void* plan, cons
 int ciaosr_linear_forward_res(const ciaosr_linear_desc* desc, const void* plan, const float* x, long long rows,
                               int activation, const float* residual, float* out, void* stream);
 
+/* The same Linear with its operand (and optionally its result) in the SPLIT representation the kernels compute in:
+ * a row-major matrix of IEEE fp16 "hi" halves and one of "lo" halves (x = hi + lo, hi = fp16(x), lo = fp16(x - hi);
+ * 22 mantissa bits), [rows, ld] with ld a multiple of 8 and columns [features, ld) zero.  Producers in this library
+ * write that form directly (ciaosr_layernorm_split_forward, ciaosr_window_attention_split_forward, this function
+ * with out == NULL), so a chain LayerNorm -> Linear -> ... never pays for re-splitting fp32 activations in the GEMM's
+ * row threads: the operand tiles are TMA-loaded straight into the UMMA layout.
+ * out != NULL: fp32 result [rows, out_features]; out == NULL: split result in out_hi / out_lo [rows, ldo]. */
+int ciaosr_linear_forward_split(const ciaosr_linear_desc* desc, const void* plan, const uint16_t* a_hi,
+                                const uint16_t* a_lo, int lda, long long rows, int activation,
+                                const float* residual, float* out, uint16_t* out_hi, uint16_t* out_lo, int ldo,
+                                void* stream);
+
 /* ---- fp32-grade 3x3 convolution on NHWC maps (SURVEY.md 8f "next" #2) -------------------------------
  * nn.Conv2d(Cin, Cout, 3, 1, 1) as the SwinIR trunk uses it after every residual Swin block group and after the body
  * (`RSTB.conv`, `conv_after_body`; swinir_net.py:446-483, 706-713 -> ciaosr_net.py:503-525), evaluated directly on
@@ -256,6 +268,13 @@ int ciaosr_window_attention_forward(const float* qkv, const float* bias_table, i
 /* nn.LayerNorm(C) of the trunk (swinir_net.py:195, 207, 702) over [rows, C] fp32, C <= 512, affine. */
 int ciaosr_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows,
                              int C, float* out, void* stream);
+
+/* split-output variants (see ciaosr_linear_forward_split): results as fp16 hi / lo halves [rows, ld], ld % 8 == 0 */
+int ciaosr_layernorm_split_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows,
+                                   int C, uint16_t* out_hi, uint16_t* out_lo, int ld, void* stream);
+int ciaosr_window_attention_split_forward(const float* qkv, const float* bias_table, int B, int H, int W, int C,
+                                          int heads, int ws, int shift, float scale, uint16_t* out_hi,
+                                          uint16_t* out_lo, int ld, void* stream);
 
 /* ---- tiled inference epilogue (ciaosr.py:218-258, 160-163) -------------- */
 /* acc/cnt [B,3,Ho,Wo] += tile prediction [B, th*tw, 3] placed at (y0,x0).   */

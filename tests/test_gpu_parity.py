@@ -748,3 +748,41 @@ def test_native_edsr_encoder_matches_pytorch():
         y0 = g.query_rgb([(ref * k).contiguous()], coord, cell)
         y1 = g.query_rgb([(out * k).contiguous()], coord, cell)
         assert max_abs(y0, y1) < TOL
+
+
+def test_native_split_activation_chain():
+    """The fp16 hi / lo split activations the SwinIR fast path passes between kernels (native.SplitTensor): LayerNorm
+    and window attention writing them, Linear reading them through TMA and writing them from its epilogue.  Each piece
+    against float64; the split form carries 22 mantissa bits, so a value v is reproduced to ~|v| * 2.4e-7."""
+    from ciaosr_b200 import native
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    for rows, c in [(1000, 180), (130, 24)]:
+        ln = torch.nn.LayerNorm(c).to(dev)
+        x = (torch.randn(rows, c, generator=g) * 2 + 0.5).to(dev)
+        st = native.layernorm_split(x, ln)
+        ref = torch.nn.functional.layer_norm(x.double(), (c,), ln.weight.double(), ln.bias.double(), ln.eps)
+        assert st.ld % 8 == 0 and st.hi.shape == (rows, st.ld)
+        assert max_abs(st.float(), ref) < 5e-6
+        assert float(st.hi[:, c:].abs().max() if st.ld > c else 0) == 0.0
+        for n, gelu in [(3 * c, False), (2 * c, True), (c, False)]:
+            wgt = (torch.randn(n, c, generator=g) / c ** 0.5).to(dev)
+            bias = (0.1 * torch.randn(n, generator=g)).to(dev)
+            res = torch.randn(rows, n, generator=g).to(dev)
+            plan = native.LinearPlan(wgt, bias)
+            want = st.float().double() @ wgt.double().t() + bias.double()
+            want = torch.nn.functional.gelu(want) if gelu else want
+            assert max_abs(plan.forward_split(st, gelu=gelu), want) < 2e-5
+            assert max_abs(plan.forward_split(st, gelu=gelu, residual=res), want + res.double()) < 2e-5
+            so = plan.forward_split(st, gelu=gelu, split_out=True)
+            assert so.features == n and max_abs(so.float(), want) < 2e-5
+            if so.ld > n:
+                assert float(so.hi[:, n:].abs().max()) == 0.0 and float(so.lo[:, n:].abs().max()) == 0.0
+    b, h, w, c, heads, ws = 1, 16, 24, 180, 6, 8
+    qkv = torch.randn(b, h * w, 3 * c, generator=g).to(dev)
+    table = (torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5).to(dev)
+    for shift in (0, 4):
+        so = native.window_attention(qkv, table, h, w, heads, ws, shift, 30 ** -0.5, split_out=True)
+        ref = _window_attention_reference(qkv, table, h, w, heads, ws, shift, 30 ** -0.5)[0]
+        assert max_abs(so.float(), ref) < 5e-6
+        assert float(so.hi[:, c:].abs().max()) == 0.0

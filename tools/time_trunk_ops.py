@@ -38,6 +38,15 @@ def main():
         r = torch.randn(rows, n, generator=g).to(dev) if res else None
         us = timed(lambda: plan.forward(x, gelu=gelu, residual=r))
         out[name] = dict(us=round(us, 1), tflops_exec=round(3 * 2 * rows * k * n / us / 1e6, 1))
+    # the same four shapes with the operand already in split form (TMA-fed A; what the block fast path runs)
+    for name, k, n, gelu, res, so in [("qkv split-in", 180, 540, False, False, False), ("proj+res split-in", 180, 180, False, True, False),
+                                      ("fc1+gelu split-in/out", 180, 360, True, False, True), ("fc2+res split-in", 360, 180, False, True, False)]:
+        a = native.SplitTensor(rows, k, dev)
+        a.hi.copy_(torch.randn(rows, a.ld, generator=g).half()); a.lo.zero_()
+        plan = native.LinearPlan((torch.randn(n, k, generator=g) / k ** 0.5).to(dev), torch.zeros(n).to(dev))
+        r = torch.randn(rows, n, generator=g).to(dev) if res else None
+        us = timed(lambda: plan.forward_split(a, gelu=gelu, residual=r, split_out=so))
+        out[name] = dict(us=round(us, 1), tflops_exec=round(3 * 2 * rows * k * n / us / 1e6, 1))
     qkv = torch.randn(b, h * w, 3 * c, generator=g).to(dev)
     table = torch.randn((2 * ws - 1) ** 2, heads, generator=g).to(dev)
     for shift in (0, 4):
@@ -46,6 +55,9 @@ def main():
     ln = torch.nn.LayerNorm(c).to(dev)
     x = torch.randn(rows, c, generator=g).to(dev)
     out["layernorm"] = dict(us=round(timed(lambda: native.layernorm(x, ln)), 1))
+    out["layernorm split-out"] = dict(us=round(timed(lambda: native.layernorm_split(x, ln)), 1))
+    out["window_attention split-out"] = dict(us=round(timed(
+        lambda: native.window_attention(qkv, table, h, w, heads, ws, 4, 30 ** -0.5, split_out=True)), 1))
     conv = torch.nn.Conv2d(c, c, 3, 1, 1).to(dev)
     cp = native.Conv3x3Plan(conv.weight, conv.bias)
     xm = x.view(b, h, w, c)
