@@ -492,12 +492,14 @@ def main():
         pair_ms = stages["pair_mlp"][0] / args.steps
         pair_launches = max(1, stages["pair_mlp"][1] // args.steps)
         fl_head = head_flops_per_query(C)                      # 8 865 280
-        fl_q = 2 * (640 * 256 + 3 * 256 * 256 + 256 * 3)       # imnet_q share, not in the pair stage
+        fused = stages["query_mlp"][1] == 0                    # head_fused_kernel: imnet_q runs inside the same kernel
+        fl_q = 0 if fused else 2 * (640 * 256 + 3 * 256 * 256 + 256 * 3)       # imnet_q share when it is a separate stage
         fl_pair = (fl_head - fl_q) * npx
         achieved = fl_pair / (pair_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "pair_mlp stage (%d launches/step)" % pair_launches,
+        kname = "head_fused_kernel" if fused else "pair_mlp_kernel"
+        roof = {"bound": "tensor", "kernel": "%s (%d launches/step)" % (kname, pair_launches),
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": ncu_traffic("pair_mlp_kernel"),
+                "frac": achieved / pk["bf16_sustained"], "traffic": ncu_traffic(kname),
                 "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic.json)",
                 "peak_source": pk["source"] + ", sustained dense bf16",
                 "algorithmic_flops_per_px": fl_head - fl_q, "ms_per_step": pair_ms,

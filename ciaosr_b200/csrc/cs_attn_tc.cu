@@ -329,41 +329,31 @@ __global__ void csa_qpatch_split_kernel(const float* __restrict__ mi, split_t* _
   *reinterpret_cast<uint2*>(q_hi + m * ldq + k) = h;
   *reinterpret_cast<uint2*>(q_lo + m * ldq + k) = l;
 }
-struct ScoreEpi {           // S[m, n] = scale * acc, n < L
+struct ScoreEpi {           // S[m, n] = scale * acc, n < L (ld % 4 == 0)
+  static constexpr bool kTile = true;
   float* s; int L, ld; float scale;
-  __device__ __forceinline__ void store(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
-    float* dst = s + m * ld + n0;
-    if (n0 + 32 <= L) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(dst)[j] =
-            make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale, v[4 * j + 3] * scale);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (n0 + i < L) dst[i] = v[i] * scale;
+  __device__ __forceinline__ void store4(long long m, int n, float4 v) const {
+    float* dst = s + m * ld + n;
+    if (n + 4 <= L) *reinterpret_cast<float4*>(dst) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    else {
+      if (n < L) dst[0] = v.x * scale;
+      if (n + 1 < L) dst[1] = v.y * scale;
+      if (n + 2 < L) dst[2] = v.z * scale;
     }
   }
 };
 struct OutEpi {             // O[m, n] = sc * acc, n < N (N % 4 == 0); accumulate: O += sc * acc (K chunks, see gemm_tc.cuh)
+  static constexpr bool kTile = true;
   float* o; int N; float sc;
-  __device__ __forceinline__ void store(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
-    float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (n0 + 4 * j < N) dst[j] = make_float4(sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
+  __device__ __forceinline__ void store4(long long m, int n, float4 v) const {
+    if (n < N) *reinterpret_cast<float4*>(o + m * N + n) = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w);
   }
-  __device__ __forceinline__ void accumulate(const TmaRowsGen::Row&, long long m, int n0, const float (&v)[32]) const {
-    float4* dst = reinterpret_cast<float4*>(o + m * N + n0);
-    float4 old[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (n0 + 4 * j < N) old[j] = dst[j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (n0 + 4 * j < N)
-        dst[j] = make_float4(fmaf(sc, v[4 * j], old[j].x), fmaf(sc, v[4 * j + 1], old[j].y),
-                             fmaf(sc, v[4 * j + 2], old[j].z), fmaf(sc, v[4 * j + 3], old[j].w));
+  __device__ __forceinline__ void accumulate4(long long m, int n, float4 v) const {
+    if (n < N) {
+      float4* dst = reinterpret_cast<float4*>(o + m * N + n);
+      const float4 old = *dst;
+      *dst = make_float4(fmaf(sc, v.x, old.x), fmaf(sc, v.y, old.y), fmaf(sc, v.z, old.z), fmaf(sc, v.w, old.w));
+    }
   }
 };
 // ---- host orchestration ------------------------------------------------------------------------------

@@ -84,6 +84,23 @@ struct agen_prefetch : std::false_type {};
 template <class AGen>
 struct agen_prefetch<AGen, std::enable_if_t<AGen::kPrefetch>> : std::true_type {};
 
+// Epi::kTile = true: the functor does not need the per-row state and offers
+//   store4(long long m, int n, float4 v)   [and accumulate4(...) when K chunking is used]
+// for 4 consecutive columns n .. n+3 of row m.  The kernel then transposes each warp's 32 x 32 accumulator chunk through
+// shared memory (XOR-swizzled 16-byte pieces, conflict-free both ways) so that a warp-wide store4 covers 4 rows x 128
+// contiguous bytes instead of 32 rows x 16 bytes: the thread-per-row pattern costs 32 memory transactions per
+// instruction and made the short-K GEMMs epilogue-bound (r02i: the row warps of the trunk's Linears were busy 83 % of the
+// kernel, the UMMA issuer 15 %).
+template <class Epi, class = void>
+struct epi_tile : std::false_type {};
+template <class Epi>
+struct epi_tile<Epi, std::enable_if_t<Epi::kTile>> : std::true_type {};
+template <class Epi, class = void>
+struct epi_tile_accumulates : std::false_type {};
+template <class Epi>
+struct epi_tile_accumulates<Epi, std::void_t<decltype(std::declval<const Epi&>().accumulate4(0LL, 0, float4{}))>>
+    : std::true_type {};
+
 template <class Epi, class Row, class = void>
 struct epi_accumulates : std::false_type {};
 template <class Epi, class Row>
@@ -134,10 +151,10 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
         for (int kc = 0; kc < n_kc; ++kc) {
           const int ns = min(kchunk, klen - kc * kchunk);
           if constexpr (agen_tma<AGen>::value)
-            produce_job_tma_a<1, TC_NEPI, true>(s, ps, afree_bits, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns,
+            produce_job_tma_a<1, TC_NEPI, false>(s, ps, afree_bits, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns,
                                                 units, 0, &map_hi, &map_lo, k0 + kc * kchunk, mt * ROWS);
           else
-            produce_job<1, true>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0);
+            produce_job<1, false>(s, ps, src + (size_t)kc * kchunk * units * UNIT_BYTES, ns, units, 0);
         }
       }
     }
@@ -150,7 +167,7 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
       k_range(job, k0, klen, kchunk, n_kc);
       for (int nc = nc0; nc < nc0 + cpj; ++nc)
         for (int kc = 0; kc < n_kc; ++kc)
-          mma_job<1, true>(s, tmem_base, m, min(kchunk, klen - kc * kchunk), min(2, g.nunits - 2 * nc),
+          mma_job<1, false>(s, tmem_base, m, min(kchunk, klen - kc * kchunk), min(2, g.nunits - 2 * nc),
                            !resident || nc == 0, !resident || nc == n_chunks - 1);
     }
   } else if (warp >= 4) {
@@ -224,14 +241,51 @@ tc_gemm_kernel(const GemmShape g, const uint8_t* __restrict__ blob, const AGen a
             }
           }
           const uint32_t d = epi_wait_d(s, e, units);
+          if constexpr (epi_tile<Epi>::value) {
+            // coalesced epilogue: lane r holds row r's 32 columns -> stage [32 rows][8 x 16 B] with piece j of row r at
+            // position j ^ (r & 7) -> lane l reads the 4 columns 4 (l & 7) .. of rows (l >> 3) + 4 i
+            const int lane = threadIdx.x & 31;
+            const uint32_t stg = smem_u32(smem) + GM_STAGE + (uint32_t)(warp - 4) * 4096u;
+            const long long m_w0 = (long long)mt * ROWS + (warp & 3) * 32;              // first row of this warp
+            const long long out_off = m_out - m;                                         // part stacking (ksplit)
 #pragma unroll 1
-          for (int cc = half; cc < units * 4; cc += 2) {
-            float v[32];
-            tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
-            if (valid) {
-              if (kc == 0) epi.store(rs, m_out, nc * 256 + cc * 32, v);
-              else if constexpr (epi_accumulates<Epi, typename AGen::Row>::value)
-                epi.accumulate(rs, m_out, nc * 256 + cc * 32, v);
+            for (int cc = half; cc < units * 4; cc += 2) {
+              float v[32];
+              tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 128u +
+                                                                               (uint32_t)((j ^ (lane & 7)) << 4)),
+                             "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                             : "memory");
+              __syncwarp();
+              const int n = nc * 256 + cc * 32 + 4 * (lane & 7);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = (lane >> 3) + 4 * i;
+                float4 q;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                             : "r"(stg + (uint32_t)rr * 128u + (uint32_t)(((lane & 7) ^ (rr & 7)) << 4))
+                             : "memory");
+                const long long mr = m_w0 + rr;
+                if (mr < g.M) {
+                  if (kc == 0) epi.store4(mr + out_off, n, q);
+                  else if constexpr (epi_tile_accumulates<Epi>::value) epi.accumulate4(mr + out_off, n, q);
+                }
+              }
+              __syncwarp();
+            }
+          } else {
+#pragma unroll 1
+            for (int cc = half; cc < units * 4; cc += 2) {
+              float v[32];
+              tmem_ld32(lane_taddr + d * 256 + cc * 32, v);
+              if (valid) {
+                if (kc == 0) epi.store(rs, m_out, nc * 256 + cc * 32, v);
+                else if constexpr (epi_accumulates<Epi, typename AGen::Row>::value)
+                  epi.accumulate(rs, m_out, nc * 256 + cc * 32, v);
+              }
             }
           }
           epi_release_d(s, e);
@@ -265,7 +319,7 @@ static int tc_gemm(const GemmShape& g, const uint8_t* blob, const AGen& agen, co
                                    !agen_combines<AGen>::value),
                  CIAOSR_E_INVALID, "tc_gemm: A-resident mode needs K <= 256, one accumulation pass and a generated A");
   if (g.kchunk > 0 && g.kchunk < g.kslabs) {
-    const bool can = epi_accumulates<Epi, typename AGen::Row>::value;
+    const bool can = epi_tile<Epi>::value ? epi_tile_accumulates<Epi>::value : epi_accumulates<Epi, typename AGen::Row>::value;
     CIAOSR_REQUIRE(can && g.kchunk % 4 == 0, CIAOSR_E_INVALID,
                    "tc_gemm: K chunking needs an accumulating epilogue and kchunk %% 4 == 0 (operand slots)");
   }

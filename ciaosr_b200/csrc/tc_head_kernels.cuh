@@ -68,51 +68,16 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
   }
 }
 
-template <int CL>
-__global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
-  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
-#ifdef CIAOSR_TC_TIMING
-  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
-#endif
-  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Row-thread work of ONE pair tile (128 (query, neighbour) rows = 32 queries): layer 1 of both chains from the LR hoists,
+// the hidden-layer epilogues, logits + softmax over the 4 neighbours, the value gather and the weighted sum -> x rows
+// [x_row0, x_row0 + 32) of P.x_hi / P.x_lo.  `cst` = the pair constants in shared memory, `bv5` = the padded last bias.
+__device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, const PairParams& P, const float* cst,
+                                               const float* bv5, uint32_t lane_taddr, int row, int half, int lane,
+                                               long long tile, long long x_row0) {
+  const int C = P.C, H = P.pc.H, W = P.pc.W;
+  const bool tap32 = (C % 32) == 0;              // a 32-column chunk never straddles a tap
   const int nchunks5 = (P.units5 + 1) / 2;
-  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
-  // tile of iteration i: clusters take CL consecutive tiles; every CTA runs `iters` iterations
-  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-
-  if (warp == 0) {
-    ProdState ps{0};
-#define PAIR_PRODUCE(b, ns, un) produce_job<CL>(s, ps, b, ns, un, cta_rank)
-    for (int it = 0; it < P.iters; ++it) {
-      const uint8_t* b = P.blob;
-      for (int j = 0; j < 6; ++j) { PAIR_PRODUCE(b, 4, 2); b += (size_t)8 * UNIT_BYTES; }
-      for (int c = 0; c < nchunks5; ++c) {
-        const int units = min(2, P.units5 - 2 * c);
-        PAIR_PRODUCE(b, 4, units);
-        b += (size_t)4 * units * UNIT_BYTES;
-      }
-    }
-  } else if (warp == 1) {
-    MmaState m{0, 0, 0};
-#define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an)
-    for (int it = 0; it < P.iters; ++it) {
-      for (int j = 0; j < 6; ++j) PAIR_MMA(4, 2, true);
-      for (int c = 0; c < nchunks5; ++c) PAIR_MMA(4, min(2, P.units5 - 2 * c), c == 0);
-    }
-  } else if (warp >= 4) {
-    const int half = (warp - 4) >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0, 0};
-    const float* cst = s.consts;
-    const float* bv5 = s.consts + 16 * HID;
-    const int C = P.C, H = P.pc.H, W = P.pc.W;
-    const bool tap32 = (C % 32) == 0;              // a 32-column chunk never straddles a tap
-    for (int it = 0; it < P.iters; ++it) {
-      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+  {
       const long long R = tile * ROWS + row;
       const bool valid = tile < P.n_tiles && R < P.total_rows;
       PairInfo p;
@@ -222,7 +187,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
           for (int g = 0; g < 8; ++g) vb[g] = value4(cp0 + 4 * g);
         }
       };
-      const long long q = R >> 2;
+      const long long q = x_row0 + (row >> 2);    // row of x for this (query, neighbour) row's query
       const int sub = (lane & 1) * 16 + ((lane >> 1) & 1) * 8;   // columns of a 32-chunk this lane ends up owning
       for (int c = 0; c < nchunks5; ++c) {
         const int units = min(2, P.units5 - 2 * c);
@@ -277,6 +242,53 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
         }
         epi_release_d(s, e);
       }
+  }
+}
+
+template <int CL>
+__global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcShared s = tc_carve(smem);
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+#ifdef CIAOSR_TC_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
+#endif
+  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks5 = (P.units5 + 1) / 2;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  // tile of iteration i: clusters take CL consecutive tiles; every CTA runs `iters` iterations
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+
+  if (warp == 0) {
+    ProdState ps{0};
+#define PAIR_PRODUCE(b, ns, un) produce_job<CL>(s, ps, b, ns, un, cta_rank)
+    for (int it = 0; it < P.iters; ++it) {
+      const uint8_t* b = P.blob;
+      for (int j = 0; j < 6; ++j) { PAIR_PRODUCE(b, 4, 2); b += (size_t)8 * UNIT_BYTES; }
+      for (int c = 0; c < nchunks5; ++c) {
+        const int units = min(2, P.units5 - 2 * c);
+        PAIR_PRODUCE(b, 4, units);
+        b += (size_t)4 * units * UNIT_BYTES;
+      }
+    }
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0};
+#define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an)
+    for (int it = 0; it < P.iters; ++it) {
+      for (int j = 0; j < 6; ++j) PAIR_MMA(4, 2, true);
+      for (int c = 0; c < nchunks5; ++c) PAIR_MMA(4, min(2, P.units5 - 2 * c), c == 0);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0, 0};
+    const float* cst = s.consts;
+    const float* bv5 = s.consts + 16 * HID;
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
     }
   }
 #ifdef CIAOSR_TC_TIMING
@@ -297,51 +309,11 @@ struct QueryParams {
   float* out; long long total_q; int n_tiles; int iters;
 };
 
-// Layer 1's A operand is x, which pair_mlp_kernel left in HBM already split into fp16 hi / lo: the producer
-// warp lands each [128 queries x 64 columns] slab pair straight in the operand slots with two 2-D TMA tile
-// loads (128B swizzle = the UMMA layout; rows past total_q read as zero), so the row threads touch layer 1
-// only to drain its accumulator.  A_READY counts NEPI/32 arrivals for the row-warp-written layers; for a TMA
-// slab the producer supplies all of them itself (one with the transaction byte count).
-template <int CL>
-__global__ void __launch_bounds__(HEAD_THREADS, 1)
-query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi,
-                 const __grid_constant__ CUtensorMap map_lo) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
-  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
-  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
-  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-
-  if (warp == 0) {
-    ProdState ps{0};
-    uint32_t afree_bits = 0xFu;            // parity to wait on next, per operand slot (same bookkeeping as the row threads)
-    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); }
-    for (int it = 0; it < P.iters; ++it) {
-      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
-      const int row0 = (int)min(tile * ROWS, (long long)0x7FFFFF00);     // past the end: all rows read as zero
-      const uint8_t* b = P.blob;
-      // layer 1: A slabs (TMA) interleaved with their weight slabs, so neither ring starves the other
-      produce_job_tma_a<CL, NEPI>(s, ps, afree_bits, b, P.slabs1, 2, cta_rank, &map_hi, &map_lo, 0, row0);
-      b += (size_t)P.slabs1 * 2 * UNIT_BYTES;
-      for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
-      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads
-    }
-  } else if (warp == 1) {
-    MmaState m{0, 0, 0};
-    for (int it = 0; it < P.iters; ++it) {
-      mma_job<CL>(s, tmem_base, m, P.slabs1, 2, true);
-      for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
-    }
-  } else if (warp >= 4) {
-    const int half = (warp - 4) >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    EpiState e{0, 0xFu, 0};                  // A_free waits start at parity 1 (fresh barrier passes)
-    const float* cst = s.consts;
-    for (int it = 0; it < P.iters; ++it) {
-      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+// Row-thread work of ONE query tile (128 queries): drain layer 1 (its operand slabs are TMA-loaded by the producer warp),
+// hidden layers 2..4, the 256 -> 3 Linear and the bilinear residual on CUDA cores -> P.out rows of tile `tile`.
+__device__ __forceinline__ void query_tile_rows(const TcShared& s, EpiState& e, const QueryParams& P, const float* cst,
+                                                uint32_t lane_taddr, int row, int half, long long tile) {
+  {
       const long long g = tile * ROWS + row;
       const bool valid = tile < P.n_tiles && g < P.total_q;
       // layer-1 operand slabs are written by the producer warp (TMA); keep the slot parity bookkeeping in step
@@ -391,6 +363,165 @@ query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi
         P.out[g * 3] = o0; P.out[g * 3 + 1] = o1; P.out[g * 3 + 2] = o2;
       }
       epi_sync<NEPI>();        // xchg is rewritten next tile
+  }
+}
+
+// Layer 1's A operand is x, which pair_mlp_kernel left in HBM already split into fp16 hi / lo: the producer
+// warp lands each [128 queries x 64 columns] slab pair straight in the operand slots with two 2-D TMA tile
+// loads (128B swizzle = the UMMA layout; rows past total_q read as zero), so the row threads touch layer 1
+// only to drain its accumulator.  A_READY counts NEPI/32 arrivals for the row-warp-written layers; for a TMA
+// slab the producer supplies all of them itself (one with the transaction byte count).
+template <int CL>
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi,
+                 const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcShared s = tc_carve(smem);
+  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+
+  if (warp == 0) {
+    ProdState ps{0};
+    uint32_t afree_bits = 0xFu;            // parity to wait on next, per operand slot (same bookkeeping as the row threads)
+    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); }
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      const int row0 = (int)min(tile * ROWS, (long long)0x7FFFFF00);     // past the end: all rows read as zero
+      const uint8_t* b = P.blob;
+      // layer 1: A slabs (TMA) interleaved with their weight slabs, so neither ring starves the other
+      produce_job_tma_a<CL, NEPI>(s, ps, afree_bits, b, P.slabs1, 2, cta_rank, &map_hi, &map_lo, 0, row0);
+      b += (size_t)P.slabs1 * 2 * UNIT_BYTES;
+      for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads
+    }
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0};
+    for (int it = 0; it < P.iters; ++it) {
+      mma_job<CL>(s, tmem_base, m, P.slabs1, 2, true);
+      for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu, 0};                  // A_free waits start at parity 1 (fresh barrier passes)
+    const float* cst = s.consts;
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
+      query_tile_rows(s, e, P, cst, lane_taddr, row, half, tile);
+    }
+  }
+  tc_teardown<CL>(tmem_base);
+}
+
+
+// =====================================================================================================
+// fused head kernel: per 128 queries, 4 pair tiles + 1 query tile in ONE persistent CTA  (opt-in)
+// =====================================================================================================
+// The two kernels above hand the attended values x [total_q, Dvp] through HBM (1.5 GB written and read back at the
+// bench size: 53x the head's algorithmic traffic, and 1.5 GB of workspace; 11.9 GB for an un-tiled x8 frame).  Here
+// every CTA alternates: four pair tiles (4 x 32 queries) write their x rows into the CTA's OWN 128-row scratch block
+// (148 x 128 rows x Dvp: 48 MB at C = 64, written and re-read by the same SM a few microseconds later, so it lives in
+// L2), then the query MLP of those 128 queries runs with its layer-1 operand TMA-loaded from that block.  Same barriers,
+// same job protocol; one more mbarrier (X_READY) orders the row threads' global stores of x before the producer's TMA
+// loads of them.
+// Measured (r02j / r02k, bench workload): 8.86 ms against 7.18 + 1.08 ms for the two kernels -- every phase switch
+// drains the operand / weight pipeline that each separate kernel keeps full across tiles, and the x loads cannot be
+// issued before x is stored.  (A variant that delays the query phase by one super-tile so that its loads are issued
+// while the current x is still being stored needed a second scratch block and a PAIR_DONE barrier and was slower
+// still: 9.65 ms.)  The x round trip of the two-kernel path costs ~0.5 ms of HBM time that overlaps with tensor work,
+// so the fused kernel is NOT the default: it is selected with CIAOSR_HEAD_FUSED=1 when workspace matters more than
+// the last 7 % of speed (its workspace is O(1) in the number of queries).
+// smem: A slots and weight ring as in tc_carve, then barriers / TMEM slot / xchg, then BOTH kernels' constants
+// (variable length, last):  [16 x 256 + Dvp pair constants][8 x 256 query constants].
+constexpr int FU_BAR = SM_W + W_STAGES * SLAB_BYTES;
+constexpr int FU_NBARS = N_BARS + 1;
+constexpr int BAR_X_READY = N_BARS;
+constexpr int FU_SLOT = FU_BAR + (FU_NBARS * 8 + 15) / 16 * 16;   // keeps everything after it 16-byte aligned
+constexpr int FU_XCHG = FU_SLOT + 16;                   // 512 floats
+constexpr int FU_CONST = FU_XCHG + 512 * 4;
+__host__ __device__ constexpr int fused_query_const_off(int Dvp) { return 16 * HID + ((Dvp + 3) / 4) * 4; }
+__host__ __device__ constexpr int fused_smem_bytes(int Dvp) { return FU_CONST + (fused_query_const_off(Dvp) + 8 * HID) * 4; }
+
+template <int CL>
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant__ CUtensorMap map_hi,
+                  const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  TcShared s;
+  {
+    const uint32_t base = smem_u32(smem);
+    s.a_hi = base + SM_A_HI; s.a_lo = base + SM_A_LO; s.w = base + SM_W;
+    s.bar = base + FU_BAR;
+    s.consts = reinterpret_cast<float*>(smem + FU_CONST);
+    s.xchg = reinterpret_cast<float*>(smem + FU_XCHG);
+  }
+  const int qoff = fused_query_const_off(P.Dvp);
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[qoff + i] = Q.consts[i];
+  if (threadIdx.x == 0) mbar_init(bar_at(s, BAR_X_READY), NEPI / 32);       // fenced + synced by the prologue below
+  const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem, FU_SLOT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks5 = (P.units5 + 1) / 2;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int scratch_row0 = blockIdx.x * ROWS;            // this CTA's block of x rows
+
+  if (warp == 0) {
+    ProdState ps{0};
+    uint32_t afree_bits = 0xFu;
+    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); }
+    for (int it = 0; it < Q.iters; ++it) {
+      for (int sub = 0; sub < 4; ++sub) {
+        const uint8_t* b = P.blob;
+        for (int j = 0; j < 6; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+        for (int c = 0; c < nchunks5; ++c) {
+          const int units = min(2, P.units5 - 2 * c);
+          produce_job<CL>(s, ps, b, 4, units, cta_rank);
+          b += (size_t)4 * units * UNIT_BYTES;
+        }
+      }
+      // x of this super-tile is complete (and visible to the async proxy) once every row warp has arrived.  All of the
+      // pair phase's A_FREE completions (an even number per slot) have happened by then, so the slot parities below
+      // continue exactly as in query_mlp_kernel.
+      mbar_wait(bar_at(s, BAR_X_READY), it & 1, 130);
+      const uint8_t* b = Q.blob;
+      produce_job_tma_a<CL, NEPI>(s, ps, afree_bits, b, Q.slabs1, 2, cta_rank, &map_hi, &map_lo, 0, scratch_row0);
+      b += (size_t)Q.slabs1 * 2 * UNIT_BYTES;
+      for (int j = 0; j < 3; ++j) { produce_job<CL>(s, ps, b, 4, 2, cta_rank); b += (size_t)8 * UNIT_BYTES; }
+      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads
+    }
+  } else if (warp == 1) {
+    MmaState m{0, 0, 0};
+    for (int it = 0; it < Q.iters; ++it) {
+      for (int sub = 0; sub < 4; ++sub) {
+        for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
+        for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+      }
+      mma_job<CL>(s, tmem_base, m, Q.slabs1, 2, true);
+      for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu, 0};                  // the pair phase toggles every slot parity an even number of times
+    const float* cst = s.consts;
+    const float* bv5 = s.consts + 16 * HID;
+    const float* qcst = s.consts + qoff;
+    for (int it = 0; it < Q.iters; ++it) {
+      const long long st = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;      // super-tile = 128 queries
+      for (int sub = 0; sub < 4; ++sub)
+        pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4));
+      // publish x: global stores (generic proxy) -> visible device-wide -> visible to the TMA engine (async proxy)
+      __threadfence();
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_at(s, BAR_X_READY));
+      query_tile_rows(s, e, Q, qcst, lane_taddr, row, half, st);
     }
   }
   tc_teardown<CL>(tmem_base);

@@ -75,10 +75,14 @@ __device__ __forceinline__ TcShared tc_carve(uint8_t* smem) {
 __device__ __forceinline__ uint32_t bar_at(const TcShared& s, int i) { return s.bar + 8u * i; }
 
 // common prologue: barrier init + TMEM allocation; returns the TMEM base address
-// smem layout of tc_gemm (gemm_tc.cuh): no per-kernel constants, six ring stages (two W_hi pairs, see w_full_bar)
-constexpr int GM_W_STAGES = 6;
-constexpr int GM_BAR = SM_W + GM_W_STAGES * SLAB_BYTES;
-constexpr int GM_SLOT = GM_BAR + N_BARS * 8;
+// smem layout of tc_gemm (gemm_tc.cuh): no per-kernel constants; the 4-stage weight ring, then a 32 KB staging area in
+// which every row warp transposes its 32 x 32 accumulator chunks so that global stores / loads of the epilogue are
+// coalesced (see tc_gemm_kernel), then barriers etc.  (A second W_hi stage pair -- W2 above -- was measured in this
+// slot first: it did not shorten the long-K GEMMs, r02e, so the space went to the epilogue, which did bound them.)
+constexpr int GM_W_STAGES = 4;
+constexpr int GM_STAGE = SM_W + GM_W_STAGES * SLAB_BYTES;       // 8 row warps x 4 KB
+constexpr int GM_BAR = GM_STAGE + 8 * 4096;
+constexpr int GM_SLOT = GM_BAR + (N_BARS * 8 + 15) / 16 * 16;
 constexpr int GM_XCHG = GM_SLOT + 16;                   // 256 floats: the two partial sums per row of combining AGens
 constexpr int GM_TOTAL = GM_XCHG + 256 * 4;
 static_assert(GM_TOTAL <= 227 * 1024, "tc_gemm shared memory exceeds the 227 KB a CTA may opt in to");

@@ -125,6 +125,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         "ciaosr_rdn_desc": (_lib.RdnDesc, ["abi_version", "mid_channels", "num_layers", "sfe1_w", "sfe2_b",
                                            "dense_w", "lff_b", "gff0_w", "gff1_b"]),
         "ciaosr_linear_desc": (_lib.LinearDesc, ["abi_version", "in_features", "out_features", "weight", "bias"]),
+        "ciaosr_conv3x3_desc": (_lib.Conv3x3Desc, ["abi_version", "in_channels", "out_channels", "weight", "bias"]),
     }
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ciaosr_b200.h"', "int main(void) {"]
     for cname, (_, fields) in probes.items():

@@ -786,3 +786,35 @@ def test_native_split_activation_chain():
         ref = _window_attention_reference(qkv, table, h, w, heads, ws, shift, 30 ** -0.5)[0]
         assert max_abs(so.float(), ref) < 5e-6
         assert float(so.hi[:, c:].abs().max()) == 0.0
+
+
+def test_fused_head_kernel_matches_two_kernel_path(monkeypatch):
+    """CIAOSR_HEAD_FUSED=1: pair tiles and the query tile of the same 128 queries in one persistent CTA with x in a
+    per-CTA, L2-resident scratch block (O(1) workspace in the number of queries).  Same arithmetic as the two-kernel
+    path, so the results must be identical bit for bit, with ragged query counts and several images."""
+    dev = _dev()
+    meta = dict(c=64, hidden=[256, 256, 256, 256], eval_bsize=30000, local_size=2, non_local=True, seed=61)
+    g = build_generator(meta, dev, engine="tcgen05")
+    plan = g.head_plan()
+    for b, h, w, s, nq in [(2, 24, 20, 4, None), (1, 16, 16, 3, 1000), (3, 9, 7, 2, 77), (1, 40, 40, 4, None)]:
+        feat = synth.synth_feature(b, 64, h, w, 61).to(dev)
+        lq = synth.synth_lr_image(b, h, w, 61).to(dev)
+        coord = make_coord((h * s, w * s)).unsqueeze(0).expand(b, -1, 2).contiguous()
+        if nq:
+            coord = coord[:, :nq].contiguous()
+        cell = make_cell((h * s, w * s), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous()
+        coord, cell = coord.to(dev), cell.to(dev)
+        nl = plan.cross_scale_attention(feat)
+        monkeypatch.delenv("CIAOSR_HEAD_FUSED", raising=False)
+        two = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        ws_two = plan.workspace_bytes(b, h, w, coord.shape[1], "tcgen05")
+        monkeypatch.setenv("CIAOSR_HEAD_FUSED", "1")
+        fused = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        ws_fused = plan.workspace_bytes(b, h, w, coord.shape[1], "tcgen05")
+        assert torch.equal(two, fused), (b, h, w, s, max_abs(two, fused))
+        if b * coord.shape[1] > 148 * 128:               # more queries than one 128-row scratch block per SM
+            assert ws_fused < ws_two
+    # the fused kernel's workspace does not grow with the number of queries
+    assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") == plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
+    monkeypatch.delenv("CIAOSR_HEAD_FUSED", raising=False)
+    assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") > 3 * plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
