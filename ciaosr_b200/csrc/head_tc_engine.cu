@@ -332,6 +332,11 @@ static int tc_grid(int n_tiles, int CL) {
   const int want = (n_tiles + CL - 1) / CL * CL;
   return want < sms ? want : sms;
 }
+// CIAOSR_HEAD_PAIR=1 (read at every call): the pair-MLP stage as CTA pairs with cta_group::2 UMMAs (pair_mlp_pair_kernel).
+static bool tc_use_pair_umma() {
+  const char* e = getenv("CIAOSR_HEAD_PAIR");
+  return e && atoi(e) == 1;
+}
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
 // the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the
 // kernel's header); ignored when its constants do not fit beside the operand slabs (very wide heads).
@@ -433,7 +438,16 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
   if ((rc = optin[0].ensure(pair_mlp_kernel<1>, SM_TOTAL)) || (rc = optin[1].ensure(pair_mlp_kernel<2>, SM_TOTAL)) ||
       (rc = optin[2].ensure(query_mlp_kernel<1>, SM_TOTAL)) || (rc = optin[3].ensure(query_mlp_kernel<2>, SM_TOTAL)))
     return rc;
-  {
+  if (tc_use_pair_umma()) {
+    StageScope sc(3, st);
+    static DynSmemOptIn optin_pair;
+    if ((rc = optin_pair.ensure(pair_mlp_pair_kernel, SM_TOTAL))) return rc;
+    CUtensorMap wmap;
+    if ((rc = tma_make_map_linear_rows(&wmap, blob + t.pair_blob, (long long)t.pair_units * 2 * ROWS))) return rc;
+    const int grid = tc_grid(P.n_tiles, 2);
+    P.iters = (P.n_tiles + grid - 1) / grid;
+    if ((rc = launch_clustered(pair_mlp_pair_kernel, grid, 2, SM_TOTAL, st, P, wmap))) return rc;
+  } else {
     StageScope sc(3, st);
     const int grid = tc_grid(P.n_tiles, CL);
     P.iters = (P.n_tiles + grid - 1) / grid;

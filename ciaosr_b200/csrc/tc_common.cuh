@@ -237,6 +237,59 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+// ---- CTA pairs (tcgen05 cta_group::2) ------------------------------------------------------------------------------
+// One UMMA spans both SMs of a cluster of two: M = 256 rows (each CTA supplies its 128 A rows from its own shared
+// memory and receives its 128 accumulator rows in its own TMEM), and each CTA stages only HALF of the B operand (N / 2
+// weight rows) at the same shared-memory offset -- the instruction reads both halves.  Per SM the operand traffic of a
+// 128 x 256 x 16 tile drops from 12 KB to 8 KB, which is what keeps a single-CTA N = 256 UMMA at ~189 cycles instead of
+// the 128 of its math (measured, profiles/r01e).  Only the leader CTA (cluster rank 0) issues; completion is
+// multicast to the mbarriers of both CTAs; the peer's row threads signal the leader's barriers with remote arrives.
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t slot_smem, uint32_t ncols) {   // the SAME warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {     // the same warp of both CTAs
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both] * B[smem of both]^T ; issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_cg2(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(desc_hi32)
+      : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` when all UMMAs issued so far by this thread completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+// arrive (release, cluster scope) on the mbarrier at local offset `bar` of CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// acquire at cluster scope: pairs with remote arrivals (try_wait defaults to CTA scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // ---- hi/lo split of an fp32 value pair ----------------------------------------------------------
 // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): the pair carries 22 mantissa bits, and
 // A*W ~= Ahi*Whi + Ahi*Wlo + Alo*Whi (3 UMMAs per product, fp32 accumulation in TMEM) is within ~2x of

@@ -64,7 +64,8 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
     }
     slab_begin(s, e, sl, false);
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    slab_done(s, sl);
+    if (s.pair_rank < 0) slab_done(s, sl);               // CTA-pair mode: two slabs per fence (see epi_hidden)
+    else if (sl & 1) slabs_done2(s, sl - 1, sl);
   }
 }
 
@@ -296,6 +297,55 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
   if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = 0;
 #endif
   tc_teardown<CL>(tmem_base);
+}
+
+// CTA-pair variant (cta_group::2, tc_pipeline.cuh "CTA-pair mode"): the two CTAs of a cluster work on 256 consecutive rows
+// with ONE M = 256 UMMA stream issued by the leader; each CTA stages half of every weight operand.  Row-thread work is
+// the same function as above (its barrier arrivals go to the leader through TcShared::pair_rank).
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  TcShared s = tc_carve(smem);
+  s.pair_rank = (int)cluster_ctarank();
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  const uint32_t tmem_base = tc_prologue_pair<NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks5 = (P.units5 + 1) / 2;
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+
+  if (warp == 0) {
+    ProdState ps{0};
+    if (lane == 0) tma_prefetch_desc(&wmap);
+    for (int it = 0; it < P.iters; ++it) {
+      long long r = 0;                                   // 128-byte row of the blob
+      for (int j = 0; j < 6; ++j) { produce_job_pair(s, ps, &wmap, r, 4, 2); r += 4 * 2 * 2 * ROWS; }
+      for (int c = 0; c < nchunks5; ++c) {
+        const int units = min(2, P.units5 - 2 * c);
+        produce_job_pair(s, ps, &wmap, r, 4, units);
+        r += 4 * units * 2 * ROWS;
+      }
+    }
+  } else if (warp == 1) {
+    if (s.pair_rank == 0) {
+      MmaState m{0, 0, 0};
+      for (int it = 0; it < P.iters; ++it) {
+        for (int j = 0; j < 6; ++j) mma_job_pair(s, tmem_base, m, 4, 2, true);
+        for (int c = 0; c < nchunks5; ++c) mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+      }
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0, 0};
+    const float* cst = s.consts;
+    const float* bv5 = s.consts + 16 * HID;
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;
+      pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
+    }
+  }
+  tc_teardown_pair(tmem_base);
 }
 
 // =====================================================================================================

@@ -61,6 +61,7 @@ struct TcShared {
   uint32_t a_hi, a_lo, w, bar;
   float* consts;
   float* xchg;
+  int pair_rank = -1;      // >= 0: CTA-pair mode (cta_group::2 UMMAs issued by rank 0): this CTA's rank in the pair
 };
 
 __device__ __forceinline__ TcShared tc_carve(uint8_t* smem) {
@@ -285,6 +286,136 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
 }
 
 
+// =====================================================================================================================
+// CTA-pair mode (cta_group::2): see tc_common.cuh.  Per CTA the weight ring holds HALF of every N = 256 operand:
+// 4 stages of 16 KB = 2 K-slabs deep ([hi | lo] x 2), twice the lookahead of the single-CTA ring in the same space.
+//   W_FULL[stage]   lives in the LEADER: 1 arrival (its producer's expect_tx) + the bytes of BOTH CTAs' tile loads
+//   W_EMPTY[stage]  in each CTA, 1 arrival: the leader's tcgen05.commit, multicast to both
+//   A_READY[slot]   in the leader, 2 x NEPI/32 arrivals (the peer's row warps arrive remotely)
+//   A_FREE / D_READY  in each CTA: multicast commits;   D_FREE[d] in the leader, 2 x NEPI/32 arrivals
+// =====================================================================================================================
+template <int NEPI>
+__device__ __forceinline__ uint32_t tc_prologue_pair(const TcShared& s, uint8_t* smem, int slot_off = SM_SLOT) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < W_STAGES + 2; ++i) { mbar_init(bar_at(s, w_full_bar(i)), 1); mbar_init(bar_at(s, w_empty_bar(i)), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_at(s, BAR_A_READY + i), 2 * NEPI / 32); mbar_init(bar_at(s, BAR_A_FREE + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_at(s, BAR_D_READY + i), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_at(s, BAR_D_FREE + i), 2 * NEPI / 32);
+    fence_mbar_init();
+  }
+  cluster_sync_all();                      // both CTAs are resident before the pair allocation
+  if (warp == 2) tmem_alloc_cg2(smem_u32(smem) + slot_off, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // peer barriers are initialised before anything signals them
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(smem + slot_off);
+}
+__device__ __forceinline__ void tc_teardown_pair(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // no CTA frees or exits while the pair may still use its TMEM / barriers
+  if ((threadIdx.x >> 5) == 2) { tc_fence_after(); tmem_dealloc_cg2(tmem_base, 512); }
+}
+
+// Weights of one job for this CTA's half of the pair.  `wmap`: un-swizzled row map over the blob (tma_make_map_linear_rows);
+// `row0`: first 128-byte row of the job in the blob (units are stored K-slab major as [hi slab][lo slab] pairs of 128 rows).
+// N = 256 jobs: the CTA takes unit `rank` (128 weight rows); N = 128 jobs: rows 64 rank .. of the single unit.
+__device__ __forceinline__ void produce_job_pair(const TcShared& s, ProdState& ps, const CUtensorMap* wmap, long long row0,
+                                                 int nslabs, int units) {
+  const bool leader_lane = (threadIdx.x & 31) == 0;
+  const int rank = s.pair_rank;
+  const uint32_t bytes = units == 2 ? SLAB_BYTES : SLAB_BYTES / 2;      // per CTA per stage
+  for (int sl = 0; sl < nslabs; ++sl) {
+    const int sp = (int)(ps.slabs & 1) * 2;
+#pragma unroll
+    for (int lo = 0; lo < 2; ++lo) {
+      const int stage = sp + lo;
+      mbar_wait(bar_at(s, w_empty_bar(stage)), ((ps.bits >> stage) & 1) ^ 1, 100 + stage);
+      ps.bits ^= 1u << stage;
+      if (leader_lane) {
+        const uint32_t full = bar_at(s, w_full_bar(stage));
+        if (rank == 0) mbar_arrive_expect_tx(full, 2 * bytes);
+        const long long r = row0 + ((long long)(sl * units + (units == 2 ? rank : 0)) * 2 + lo) * ROWS +
+                            (units == 2 ? 0 : 64 * rank);
+        const uint32_t dst = s.w + stage * SLAB_BYTES;
+        tma_load_2d_cg2(dst, wmap, 0, (int)r, full);
+        if (units == 2) tma_load_2d_cg2(dst + SLAB_BYTES / 2, wmap, 0, (int)r + 64, full);
+      }
+      __syncwarp();
+    }
+    ++ps.slabs;
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+#ifdef CIAOSR_TC_TIMING
+  const long long tt = clock64();
+  struct Rec { int tag; long long t; __device__ ~Rec() { tc_time_add(tag / 10, t); } } rec{tag, tt};
+#endif
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("ciaosr tcgen05: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// one job of the pair, issued by the leader's warp 1:  D[jobctr & 1] of BOTH CTAs = A (256 rows) * W^T
+__device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_base, MmaState& m, int nslabs, int units,
+                                             bool a_new, bool a_release = true) {
+  const bool leader = (threadIdx.x & 31) == 0;
+  const uint32_t idesc = make_idesc_split(2 * ROWS, UNIT_N * units);
+  const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
+  mbar_wait_cluster(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
+  tc_fence_after();
+  const uint32_t dcol = tmem_base + d * 256;
+  for (int sl = 0; sl < nslabs; ++sl) {
+    const int slot = sl & 3;
+    const int sp = (int)(m.slabs & 1) * 2;
+    if (a_new) {
+      mbar_wait_cluster(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
+      m.aready_bits ^= 1u << slot;
+    }
+    const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
+    const uint32_t b_hi = desc_lo(s.w + sp * SLAB_BYTES), b_lo = desc_lo(s.w + (sp + 1) * SLAB_BYTES);
+    mbar_wait(bar_at(s, w_full_bar(sp)), (m.wbits >> sp) & 1, 220);
+    m.wbits ^= 1u << sp;
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        umma_cg2(dcol, a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, (sl | ks) != 0 ? 1u : 0u);
+        umma_cg2(dcol, a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, 1u);
+      }
+      umma_commit_cg2(bar_at(s, w_empty_bar(sp)), 3);
+    }
+    __syncwarp();
+    mbar_wait(bar_at(s, w_full_bar(sp + 1)), (m.wbits >> (sp + 1)) & 1, 222);
+    m.wbits ^= 1u << (sp + 1);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) umma_cg2(dcol, a_hi + 2 * ks, b_lo + 2 * ks, DESC_HI, idesc, 1u);
+      umma_commit_cg2(bar_at(s, w_empty_bar(sp + 1)), 3);
+      if (a_release) umma_commit_cg2(bar_at(s, BAR_A_FREE + slot), 3);
+    }
+    __syncwarp();
+    ++m.slabs;
+  }
+  if (leader) {
+    umma_commit_cg2(bar_at(s, BAR_D_READY + 2 * d), 3);
+    if (units == 2) umma_commit_cg2(bar_at(s, BAR_D_READY + 2 * d + 1), 3);
+  }
+  __syncwarp();
+  ++m.jobctr;
+}
+
 // ---- row-thread helpers --------------------------------------------------------------------------------
 // afree_bits / dready_bits: parity to wait on next, per operand slot / per (accumulator, column half)
 struct EpiState { uint32_t jobctr; uint32_t afree_bits; uint32_t dready_bits; };
@@ -297,17 +428,22 @@ __device__ __forceinline__ void slab_begin(const TcShared& s, EpiState& e, int s
 // the async proxy (fence.proxy.async, ONE per call: it drains the thread's outstanding shared stores
 // and is the most expensive instruction of the epilogue), the warp converges, and one lane arrives
 // (A_READY counts warps, not threads: same-address mbarrier arrivals serialise).
+// arrive on the barrier the UMMA issuer waits on: the CTA's own, or the leader's in CTA-pair mode
+__device__ __forceinline__ void arrive_issuer(const TcShared& s, int idx) {
+  if (s.pair_rank <= 0) mbar_arrive(bar_at(s, idx));
+  else mbar_arrive_cluster(bar_at(s, idx), 0);
+}
 __device__ __forceinline__ void slab_done(const TcShared& s, int slot) {
   fence_proxy_async();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(bar_at(s, BAR_A_READY + slot));
+  if ((threadIdx.x & 31) == 0) arrive_issuer(s, BAR_A_READY + slot);
 }
 __device__ __forceinline__ void slabs_done2(const TcShared& s, int slot_a, int slot_b) {
   fence_proxy_async();
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
-    mbar_arrive(bar_at(s, BAR_A_READY + slot_a));
-    mbar_arrive(bar_at(s, BAR_A_READY + slot_b));
+    arrive_issuer(s, BAR_A_READY + slot_a);
+    arrive_issuer(s, BAR_A_READY + slot_b);
   }
 }
 // wait until column half `nh` of the current job's accumulator is complete; returns the accumulator index
@@ -333,7 +469,7 @@ __device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
   if (threadIdx.x == EPI_T0) TC_TRACE(2010);           // rows: accumulator drained
   tc_fence_before();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(bar_at(s, BAR_D_FREE + (e.jobctr & 1)));
+  if ((threadIdx.x & 31) == 0) arrive_issuer(s, BAR_D_FREE + (e.jobctr & 1));
   ++e.jobctr;
 }
 
@@ -370,8 +506,13 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
       v[4 * j + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 3]) + b4.w, 0.0f);
     }
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
-    if (HALVES == 2) slab_done(s, sl);      // per slab: the next layer's first UMMAs start one slab earlier (-3 % kernel time)
-    else if (c & 1) slab_done(s, sl);
+    if (HALVES == 2) {
+      // single-CTA mode: per slab -- the next layer's first UMMAs start one slab earlier (-3 % kernel time).  CTA-pair
+      // mode: the M = 256 UMMAs are ~3x cheaper per row and the ROW threads are the critical path (r02n: issuer idle
+      // 63 %), so they publish two slabs per fence.proxy.async (the most expensive step of this epilogue) instead.
+      if (s.pair_rank < 0) slab_done(s, sl);
+      else if (c & 1) slabs_done2(s, sl - 1, sl);
+    } else if (c & 1) slab_done(s, sl);
   }
   epi_release_d(s, e);
 }

@@ -818,3 +818,29 @@ def test_fused_head_kernel_matches_two_kernel_path(monkeypatch):
     assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") == plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
     monkeypatch.delenv("CIAOSR_HEAD_FUSED", raising=False)
     assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") > 3 * plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
+
+
+def test_cta_pair_umma_path_matches_default(monkeypatch):
+    """CIAOSR_HEAD_PAIR=1: the pair-MLP stage with cta_group::2 UMMAs (M = 256 across the two CTAs of a cluster, each
+    staging half of every weight operand).  Same products, same accumulation order per output element as the
+    single-CTA path, so the outputs are expected to agree to the last bit (1e-6 is asserted)."""
+    dev = _dev()
+    meta = dict(c=64, hidden=[256, 256, 256, 256], eval_bsize=30000, local_size=2, non_local=True, seed=71)
+    g = build_generator(meta, dev, engine="tcgen05")
+    plan = g.head_plan()
+    for b, h, w, s, nq in [(2, 24, 20, 4, None), (1, 9, 7, 2, 77), (1, 40, 40, 4, None)]:
+        feat = synth.synth_feature(b, 64, h, w, 71).to(dev)
+        lq = synth.synth_lr_image(b, h, w, 71).to(dev)
+        coord = make_coord((h * s, w * s)).unsqueeze(0).expand(b, -1, 2).contiguous()
+        if nq:
+            coord = coord[:, :nq].contiguous()
+        cell = make_cell((h * s, w * s), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous()
+        coord, cell = coord.to(dev), cell.to(dev)
+        nl = plan.cross_scale_attention(feat)
+        monkeypatch.delenv("CIAOSR_HEAD_PAIR", raising=False)
+        ref = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        monkeypatch.setenv("CIAOSR_HEAD_PAIR", "1")
+        out = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        torch.cuda.synchronize()
+        print(f"CTA-pair UMMA path {b}x{h}x{w} x{s}: max-abs vs single-CTA path {max_abs(out, ref):.2e}")
+        assert max_abs(out, ref) < 1e-6
