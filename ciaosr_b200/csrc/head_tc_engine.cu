@@ -332,10 +332,11 @@ static int tc_grid(int n_tiles, int CL) {
   const int want = (n_tiles + CL - 1) / CL * CL;
   return want < sms ? want : sms;
 }
-// CIAOSR_HEAD_PAIR=1 (read at every call): the pair-MLP stage as CTA pairs with cta_group::2 UMMAs (pair_mlp_pair_kernel).
+// The pair-MLP stage runs as CTA pairs with cta_group::2 UMMAs (pair_mlp_pair_kernel) unless CIAOSR_HEAD_PAIR=0 (read at
+// every call) selects the single-CTA kernel with multicast weights.
 static bool tc_use_pair_umma() {
   const char* e = getenv("CIAOSR_HEAD_PAIR");
-  return e && atoi(e) == 1;
+  return !(e && atoi(e) == 0);
 }
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
 // the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the

@@ -271,11 +271,15 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
-// arrive (release, cluster scope) on the mbarrier at local offset `bar` of CTA `rank` of this cluster
+// arrive on the mbarrier at local offset `bar` of CTA `rank` of this cluster.  RELAXED on purpose: a release at cluster
+// scope compiles to MEMBAR + ERRBAR + CCTL.IVALL (it drains the thread's memory operations and invalidates the SM's L1,
+// 11 % of all stall samples of the first pair-mode kernel, r02p), and nothing the waiter reads through the generic proxy
+// depends on it: operand slabs are published to the tensor core by fence.proxy.async before the arrive, accumulator
+// reads are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) before it.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // acquire at cluster scope: pairs with remote arrivals (try_wait defaults to CTA scope)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -288,6 +292,34 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2, one issue slot for two IEEE fp32 operations) ------------------
+// The row threads of the head kernels are issue-bound once the UMMAs are cheap (CTA-pair mode, r02p: 147 k warp
+// instructions per tile at IPC 1.4); their element-wise work -- bias adds, the layer-1 FMAs, the v - hi subtractions of
+// the operand split -- runs on pairs.  Results are bit-identical to the scalar forms (same rounding, no contraction).
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 
 // ---- hi/lo split of an fp32 value pair ----------------------------------------------------------
@@ -311,7 +343,9 @@ __host__ __device__ inline void split_scalar(float w, split_t& hi, split_t& lo) 
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
   const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h.y), "f"(v0 - h.x));
+  float d0, d1;
+  unpack2(sub2(pack2(v0, v1), pack2(h.x, h.y)), d0, d1);          // one FADD2 for both residuals
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 }
 __device__ inline void split_scalar(float w, split_t& hi, split_t& lo) {
   hi = __float2half_rn(fminf(fmaxf(w, -65504.0f), 65504.0f));

@@ -372,14 +372,14 @@ __device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_ba
   const bool leader = (threadIdx.x & 31) == 0;
   const uint32_t idesc = make_idesc_split(2 * ROWS, UNIT_N * units);
   const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
-  mbar_wait_cluster(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
+  mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);        // CTA-scope acquire: see mbar_arrive_cluster
   tc_fence_after();
   const uint32_t dcol = tmem_base + d * 256;
   for (int sl = 0; sl < nslabs; ++sl) {
     const int slot = sl & 3;
     const int sp = (int)(m.slabs & 1) * 2;
     if (a_new) {
-      mbar_wait_cluster(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
+      mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
       m.aready_bits ^= 1u << slot;
     }
     const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
@@ -500,10 +500,13 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b4 = reinterpret_cast<const float4*>(bias_s + col)[j];
-      v[4 * j] = fmaxf(__uint_as_float(buf[c & 1][4 * j]) + b4.x, 0.0f);
-      v[4 * j + 1] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 1]) + b4.y, 0.0f);
-      v[4 * j + 2] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 2]) + b4.z, 0.0f);
-      v[4 * j + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * j + 3]) + b4.w, 0.0f);
+      float t0, t1, t2, t3;                      // bias add on pairs (FADD2), ReLU per element
+      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j]), __uint_as_float(buf[c & 1][4 * j + 1])), pack2(b4.x, b4.y)), t0, t1);
+      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j + 2]), __uint_as_float(buf[c & 1][4 * j + 3])), pack2(b4.z, b4.w)), t2, t3);
+      v[4 * j] = fmaxf(t0, 0.0f);
+      v[4 * j + 1] = fmaxf(t1, 0.0f);
+      v[4 * j + 2] = fmaxf(t2, 0.0f);
+      v[4 * j + 3] = fmaxf(t3, 0.0f);
     }
     a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
     if (HALVES == 2) {

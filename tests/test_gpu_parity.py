@@ -687,6 +687,7 @@ def test_native_window_attention(c, heads, ws, h, w, b):
 def test_native_layernorm_conv3x3_and_fused_residuals():
     from ciaosr_b200 import native
     dev = _dev()
+    torch.manual_seed(5)                      # nn.Conv2d / nn.LayerNorm initialise from the global generator
     g = torch.Generator().manual_seed(5)
     # LayerNorm
     for rows, c in [(1000, 180), (37, 24), (5, 512)]:
@@ -705,8 +706,10 @@ def test_native_layernorm_conv3x3_and_fused_residuals():
         plan = native.Conv3x3Plan(conv.weight, conv.bias)
         ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), conv.bias.double(),
                                          padding=1).permute(0, 2, 3, 1)
-        assert max_abs(plan.forward(x), ref) < 2e-5
-        assert max_abs(plan.forward(x, residual=res), ref + res.double()) < 2e-5
+        # K = 9 Cin up to 1620: ~300 truncating TMEM accumulation steps of up to 1 ulp each
+        tol = 4e-5 * max(1.0, float(ref.abs().max()))
+        assert max_abs(plan.forward(x), ref) < tol
+        assert max_abs(plan.forward(x, residual=res), ref + res.double()) < tol
     # Linear with fused residual; short K with several N-chunks runs in the A-resident mode
     for rows, k, n in [(700, 180, 540), (129, 180, 360), (64, 360, 180), (300, 24, 72)]:
         x = torch.randn(rows, k, generator=g).to(dev)
@@ -821,7 +824,7 @@ def test_fused_head_kernel_matches_two_kernel_path(monkeypatch):
 
 
 def test_cta_pair_umma_path_matches_default(monkeypatch):
-    """CIAOSR_HEAD_PAIR=1: the pair-MLP stage with cta_group::2 UMMAs (M = 256 across the two CTAs of a cluster, each
+    """Default vs CIAOSR_HEAD_PAIR=0: the pair-MLP stage with cta_group::2 UMMAs (M = 256 across the two CTAs of a cluster, each
     staging half of every weight operand).  Same products, same accumulation order per output element as the
     single-CTA path, so the outputs are expected to agree to the last bit (1e-6 is asserted)."""
     dev = _dev()
@@ -837,9 +840,9 @@ def test_cta_pair_umma_path_matches_default(monkeypatch):
         cell = make_cell((h * s, w * s), coord.shape[1]).unsqueeze(0).expand(b, -1, 2).contiguous()
         coord, cell = coord.to(dev), cell.to(dev)
         nl = plan.cross_scale_attention(feat)
-        monkeypatch.delenv("CIAOSR_HEAD_PAIR", raising=False)
+        monkeypatch.setenv("CIAOSR_HEAD_PAIR", "0")
         ref = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
-        monkeypatch.setenv("CIAOSR_HEAD_PAIR", "1")
+        monkeypatch.delenv("CIAOSR_HEAD_PAIR", raising=False)             # default: CTA pairs
         out = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
         torch.cuda.synchronize()
         print(f"CTA-pair UMMA path {b}x{h}x{w} x{s}: max-abs vs single-CTA path {max_abs(out, ref):.2e}")
