@@ -496,7 +496,8 @@ def main():
         fl_q = 0 if fused else 2 * (640 * 256 + 3 * 256 * 256 + 256 * 3)       # imnet_q share when it is a separate stage
         fl_pair = (fl_head - fl_q) * npx
         achieved = fl_pair / (pair_ms * 1e-3) / 1e12
-        kname = "head_fused_kernel" if fused else "pair_mlp_kernel"
+        pair_mode = os.environ.get("CIAOSR_HEAD_PAIR", "1") != "0"      # default: CTA pairs, cta_group::2 UMMAs
+        kname = "head_fused_kernel" if fused else ("pair_mlp_pair_kernel" if pair_mode else "pair_mlp_kernel")
         roof = {"bound": "tensor", "kernel": "%s (%d launches/step)" % (kname, pair_launches),
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"], "traffic": ncu_traffic(kname),

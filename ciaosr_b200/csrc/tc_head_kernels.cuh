@@ -123,12 +123,16 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
           if (sl + 1 < 4) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
           const int c0 = sl * 64 + half * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; ++j) {               // bias adds on pairs; the logit sum keeps its sequential order
             const float4 g = gb[j];
-            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j]) + bias_s[c0 + 4 * j], 0.0f), g.x, logit);
-            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 1]) + bias_s[c0 + 4 * j + 1], 0.0f), g.y, logit);
-            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 2]) + bias_s[c0 + 4 * j + 2], 0.0f), g.z, logit);
-            logit = fmaf(fmaxf(__uint_as_float(buf[sl & 1][4 * j + 3]) + bias_s[c0 + 4 * j + 3], 0.0f), g.w, logit);
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+            float h0, h1, h2, h3;
+            unpack2(add2(pack2(__uint_as_float(buf[sl & 1][4 * j]), __uint_as_float(buf[sl & 1][4 * j + 1])), pack2(b4.x, b4.y)), h0, h1);
+            unpack2(add2(pack2(__uint_as_float(buf[sl & 1][4 * j + 2]), __uint_as_float(buf[sl & 1][4 * j + 3])), pack2(b4.z, b4.w)), h2, h3);
+            logit = fmaf(fmaxf(h0, 0.0f), g.x, logit);
+            logit = fmaf(fmaxf(h1, 0.0f), g.y, logit);
+            logit = fmaf(fmaxf(h2, 0.0f), g.z, logit);
+            logit = fmaf(fmaxf(h3, 0.0f), g.w, logit);
           }
           if (sl + 1 < 4) {
 #pragma unroll
@@ -218,14 +222,20 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
           }
           tmem_ld32_wait(buf[k & 1]);
           if ((k & 1) == 0) tmem_ld32_issue(lane_taddr + d * 256 + (cc + 2) * 32, buf[(k + 1) & 1]);
+          const uint64_t aa = pack2(a, a);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < 8; ++g) {               // (a * value) * (acc + bias), two columns per instruction
             const float4 val = vb[g];
             const int o = cp0 + 4 * g;
-            v[4 * g] = a * val.x * (__uint_as_float(buf[k & 1][4 * g]) + bv5[o]);
-            v[4 * g + 1] = a * val.y * (__uint_as_float(buf[k & 1][4 * g + 1]) + bv5[o + 1]);
-            v[4 * g + 2] = a * val.z * (__uint_as_float(buf[k & 1][4 * g + 2]) + bv5[o + 2]);
-            v[4 * g + 3] = a * val.w * (__uint_as_float(buf[k & 1][4 * g + 3]) + bv5[o + 3]);
+            const float4 b4 = *reinterpret_cast<const float4*>(bv5 + o);
+            unpack2(mul2(mul2(aa, pack2(val.x, val.y)),
+                         add2(pack2(__uint_as_float(buf[k & 1][4 * g]), __uint_as_float(buf[k & 1][4 * g + 1])),
+                              pack2(b4.x, b4.y))),
+                    v[4 * g], v[4 * g + 1]);
+            unpack2(mul2(mul2(aa, pack2(val.z, val.w)),
+                         add2(pack2(__uint_as_float(buf[k & 1][4 * g + 2]), __uint_as_float(buf[k & 1][4 * g + 3])),
+                              pack2(b4.z, b4.w))),
+                    v[4 * g + 2], v[4 * g + 3]);
           }
           if (k + 1 < nsub) load_values(cp0 + 64, vb);
           // sum over the 4 neighbour rows (lanes 4q..4q+3), leaving each lane with 8 of the 32 columns
