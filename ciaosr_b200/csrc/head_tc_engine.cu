@@ -338,6 +338,19 @@ static bool tc_use_pair_umma() {
   const char* e = getenv("CIAOSR_HEAD_PAIR");
   return !(e && atoi(e) == 0);
 }
+// Experiment switches of the CTA-pair kernel, both measured slower than the default on the bench workload:
+// CIAOSR_HEAD_ROWPARTS=4: four row threads per row (16 row warps) instead of two -- the row threads are bound by the
+// half-rate ALU / conversion pipes, not by latency, so twice the warps convert a slab in the same time (6.91 vs 6.83 ms);
+// CIAOSR_HEAD_NSPLIT=1: two N = 128 column halves per layer with the first half's epilogue under the second half's
+// UMMAs -- fewer bubbles, but N = 128 UMMAs cost 106 cycles in the kernel against 2 x 74 ideal (6.91 vs 6.75 ms).
+static int tc_row_parts() {
+  const char* e = getenv("CIAOSR_HEAD_ROWPARTS");
+  return (e && atoi(e) == 4) ? 4 : 2;
+}
+static bool tc_nsplit() {
+  const char* e = getenv("CIAOSR_HEAD_NSPLIT");
+  return e && atoi(e) == 1;
+}
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
 // the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the
 // kernel's header); ignored when its constants do not fit beside the operand slabs (very wide heads).
@@ -372,9 +385,10 @@ size_t head_tc_workspace(const PlanLayout& L, int B, int H, int W, int Q) {
 }
 
 template <class Kernel, class... Args>
-static int launch_clustered(Kernel kernel, int grid, int CL, int smem_bytes, cudaStream_t st, const Args&... args) {
+static int launch_clustered_t(Kernel kernel, int grid, int CL, int threads, int smem_bytes, cudaStream_t st,
+                              const Args&... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(HEAD_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -386,6 +400,11 @@ static int launch_clustered(Kernel kernel, int grid, int CL, int smem_bytes, cud
     return CIAOSR_E_CUDA;
   }
   return CIAOSR_OK;
+}
+
+template <class Kernel, class... Args>
+static int launch_clustered(Kernel kernel, int grid, int CL, int smem_bytes, cudaStream_t st, const Args&... args) {
+  return launch_clustered_t(kernel, grid, CL, HEAD_THREADS, smem_bytes, st, args...);
 }
 
 int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void* ws, size_t ws_bytes,
@@ -441,13 +460,23 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     return rc;
   if (tc_use_pair_umma()) {
     StageScope sc(3, st);
-    static DynSmemOptIn optin_pair;
-    if ((rc = optin_pair.ensure(pair_mlp_pair_kernel, SM_TOTAL))) return rc;
+    static DynSmemOptIn optin_pair[4];
+    if ((rc = optin_pair[0].ensure(pair_mlp_pair_kernel<2, false>, SM_TOTAL)) ||
+        (rc = optin_pair[1].ensure(pair_mlp_pair_kernel<4, false>, SM_TOTAL)) ||
+        (rc = optin_pair[2].ensure(pair_mlp_pair_kernel<2, true>, SM_TOTAL)) ||
+        (rc = optin_pair[3].ensure(pair_mlp_pair_kernel<4, true>, SM_TOTAL)))
+      return rc;
     CUtensorMap wmap;
     if ((rc = tma_make_map_linear_rows(&wmap, blob + t.pair_blob, (long long)t.pair_units * 2 * ROWS))) return rc;
     const int grid = tc_grid(P.n_tiles, 2);
     P.iters = (P.n_tiles + grid - 1) / grid;
-    if ((rc = launch_clustered(pair_mlp_pair_kernel, grid, 2, SM_TOTAL, st, P, wmap))) return rc;
+    if (tc_nsplit())
+      rc = tc_row_parts() == 4 ? launch_clustered_t(pair_mlp_pair_kernel<4, true>, grid, 2, 640, SM_TOTAL, st, P, wmap)
+                               : launch_clustered_t(pair_mlp_pair_kernel<2, true>, grid, 2, 384, SM_TOTAL, st, P, wmap);
+    else
+      rc = tc_row_parts() == 4 ? launch_clustered_t(pair_mlp_pair_kernel<4, false>, grid, 2, 640, SM_TOTAL, st, P, wmap)
+                               : launch_clustered_t(pair_mlp_pair_kernel<2, false>, grid, 2, 384, SM_TOTAL, st, P, wmap);
+    if (rc) return rc;
   } else {
     StageScope sc(3, st);
     const int grid = tc_grid(P.n_tiles, CL);
@@ -479,6 +508,11 @@ extern "C" int ciaosr_debug_trace(int on, unsigned long long* out, unsigned int*
   unsigned int z = 0;
   cudaMemcpyToSymbol(ciaosr::tc::g_trace_n, &z, 4);
   cudaMemcpyToSymbol(ciaosr::tc::g_trace_req, &on, 4);
+  return 0;
+}
+extern "C" int ciaosr_debug_flags(int flags) {
+  cudaDeviceSynchronize();
+  cudaMemcpyToSymbol(ciaosr::tc::g_dbg_flags, &flags, 4);
   return 0;
 }
 // diagnostic build only: cycles spent in mbarrier waits by the kernels of this translation unit

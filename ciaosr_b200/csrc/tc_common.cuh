@@ -70,12 +70,17 @@ __device__ __forceinline__ void tc_trace(int tag) {
   }
 }
 #define TC_TRACE(tag) ::ciaosr::tc::tc_trace(tag)
+// experiment switches of the diagnostic build (ciaosr_debug_flags): bit 0 = row threads skip their arithmetic and operand
+// stores (waits / arrivals kept), bit 1 = the weight producer of the CTA-pair kernel signals stages without loading them
+static __device__ int g_dbg_flags;
+#define TC_DBG(bit) (::ciaosr::tc::g_dbg_flags & (bit))
 #else
+#define TC_DBG(bit) 0
 #define TC_TRACE(tag) do {} while (0)
 #endif
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-#ifdef CIAOSR_TC_TIMING
+#if defined(CIAOSR_TC_TIMING) && !defined(CIAOSR_TC_TRACE_ONLY)      // TRACE_ONLY: timeline events without the wait counters
   const long long tt = clock64();
   struct Rec { int tag; long long t; __device__ ~Rec() { tc_time_add(tag / 10, t); } } rec{tag, tt};
 #endif
@@ -165,6 +170,30 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+
+// 16-column forms (four row threads per row: each thread owns a 16-column quarter of every 64-column slab)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15])
+               :
+               : "memory");
+}
+// width-generic spellings used by the row-thread code (N = 16 or 32 columns per chunk)
+__device__ __forceinline__ void tmem_ldN_issue(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldN_issue(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ldN_wait(uint32_t (&r)[32]) { tmem_ld32_wait(r); }
+__device__ __forceinline__ void tmem_ldN_wait(uint32_t (&r)[16]) { tmem_ld16_wait(r); }
 
 // ---- clusters ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -378,6 +407,30 @@ __device__ __forceinline__ void a_store32(uint32_t slab_hi, uint32_t slab_lo, in
                  : "memory");
   }
 }
+
+// 16 consecutive K-columns [c0, c0+16) (c0 % 16 == 0): two 16-byte chunks per half
+template <class T>
+__device__ __forceinline__ void a_store16(uint32_t slab_hi, uint32_t slab_lo, int row, int c0,
+                                          const T (&v)[16]) {
+  const uint32_t rbase = (uint32_t)row * 128u;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+    const uint32_t chunk = (uint32_t)(((c0 >> 3) + j) ^ (row & 7)) << 4;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_hi + rbase + chunk), "r"(h[0]),
+                 "r"(h[1]), "r"(h[2]), "r"(h[3])
+                 : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_lo + rbase + chunk), "r"(l[0]),
+                 "r"(l[1]), "r"(l[2]), "r"(l[3])
+                 : "memory");
+  }
+}
+template <class T>
+__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[32]) { a_store32(hi, lo, row, c0, v); }
+template <class T>
+__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[16]) { a_store16(hi, lo, row, c0, v); }
 
 // byte offset of element (n, k) inside a [128 x 64] SW128 slab (used by the weight packer)
 __host__ __device__ inline uint32_t sw128_offset(int n, int k) {

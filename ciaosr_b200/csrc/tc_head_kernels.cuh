@@ -35,28 +35,31 @@ struct PairParams {
 //                               then bv5p[Dvp] (last value Linear bias, tap-major, zero padded)
 
 // layer 1 of imnet_k / imnet_v from the LR hoist:  relu(P[pix] + b1 + rc . [rel_y, rel_x, sc_y, sc_x])
+// PARTS = row threads per row (2 or 4); `half` = this thread's part: columns [CW*half, CW*half + CW) of every slab
+template <int PARTS>
 __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
                                            const float* __restrict__ P, const float* __restrict__ rc_s,
                                            const float* __restrict__ b1_s) {
-  const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * 8 : nullptr;
-  float4 buf[8];
+  constexpr int CW = 64 / PARTS, NV = CW / 4;
+  const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * NV : nullptr;
+  float4 buf[NV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) buf[j] = prow ? __ldg(prow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NV; ++j) buf[j] = prow ? __ldg(prow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int sl = 0; sl < 4; ++sl) {
-    float v[32];
+    float v[CW];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { v[4 * j] = buf[j].x; v[4 * j + 1] = buf[j].y; v[4 * j + 2] = buf[j].z; v[4 * j + 3] = buf[j].w; }
+    for (int j = 0; j < NV; ++j) { v[4 * j] = buf[j].x; v[4 * j + 1] = buf[j].y; v[4 * j + 2] = buf[j].z; v[4 * j + 3] = buf[j].w; }
     if (sl + 1 < 4) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) buf[j] = prow ? __ldg(prow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j) buf[j] = prow ? __ldg(prow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const int c0 = sl * 64 + half * 32;
+    const int c0 = sl * 64 + half * CW;
     // same operations in the same order as the scalar form, two columns per instruction (FADD2 / FFMA2)
     const uint64_t ry = pack2(p.rel_y, p.rel_y), rx = pack2(p.rel_x, p.rel_x);
     const uint64_t sy = pack2(p.sc_y, p.sc_y), sx = pack2(p.sc_x, p.sc_x);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < CW; i += 2) {
       const int c = c0 + i;
       const float2 b1 = *reinterpret_cast<const float2*>(b1_s + c);
       const float2 r0 = *reinterpret_cast<const float2*>(rc_s + c), r1 = *reinterpret_cast<const float2*>(rc_s + HID + c);
@@ -72,8 +75,8 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
       v[i + 1] = fmaxf(t1, 0.0f);
     }
     slab_begin(s, e, sl, false);
-    a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * 32, v);
-    if (s.pair_rank < 0) slab_done(s, sl);               // CTA-pair mode: two slabs per fence (see epi_hidden)
+    if (!TC_DBG(1)) a_storeN(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * CW, v);
+    if (s.pair_rank < 0 || sl < 2) slab_done(s, sl);     // CTA-pair mode: slabs 2 + 3 share a fence (see epi_hidden)
     else if (sl & 1) slabs_done2(s, sl - 1, sl);
   }
 }
@@ -81,11 +84,14 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
 // Row-thread work of ONE pair tile (128 (query, neighbour) rows = 32 queries): layer 1 of both chains from the LR hoists,
 // the hidden-layer epilogues, logits + softmax over the 4 neighbours, the value gather and the weighted sum -> x rows
 // [x_row0, x_row0 + 32) of P.x_hi / P.x_lo.  `cst` = the pair constants in shared memory, `bv5` = the padded last bias.
+// PARTS = row threads per row (2: 32-column chunks, 4: 16-column chunks); `half` = this thread's part index.
+template <int PARTS>
 __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, const PairParams& P, const float* cst,
                                                const float* bv5, uint32_t lane_taddr, int row, int half, int lane,
                                                long long tile, long long x_row0) {
   const int C = P.C, H = P.pc.H, W = P.pc.W;
-  const bool tap32 = (C % 32) == 0;              // a 32-column chunk never straddles a tap
+  constexpr int CW = 64 / PARTS, NV = CW / 4;    // columns / float4s per chunk
+  const bool tap32 = (C % CW) == 0;              // a chunk never straddles a tap
   const int nchunks5 = (P.units5 + 1) / 2;
   {
       const long long R = tile * ROWS + row;
@@ -96,34 +102,34 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
 
       // ---- key chain -----------------------------------------------------------------------
       if (threadIdx.x == EPI_T0) TC_TRACE(3000);       // tile start
-      gen_layer1(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
+      gen_layer1<PARTS>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
       if (threadIdx.x == EPI_T0) TC_TRACE(3001);       // k.L1 written
-      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 5 * HID);
-      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 6 * HID);
+      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 5 * HID);
+      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 6 * HID);
       // k.L4 is complete once both accumulator halves are; that also frees the operand slabs, so the value
       // chain's layer 1 is built FIRST: the UMMAs of v.L2 then run while the logits are reduced from D.
       const uint32_t dk = epi_wait_half(s, e, 0);
       epi_wait_half(s, e, 1);
       if (threadIdx.x == EPI_T0) TC_TRACE(3002);       // k.L4 complete
-      gen_layer1(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      gen_layer1<PARTS>(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
       if (threadIdx.x == EPI_T0) TC_TRACE(3003);       // v.L1 written
       float logit = 0.0f;
       {
         const uint32_t d = dk;
         const float* bias_s = cst + 7 * HID;
-        const float4* grow = p.gidx >= 0 ? reinterpret_cast<const float4*>(P.G + (long long)p.gidx * P.ldg) + half * 8 : nullptr;
-        uint32_t buf[2][32];
-        float4 gb[8];
-        tmem_ld32_issue(lane_taddr + d * 256 + half * 32, buf[0]);
+        const float4* grow = p.gidx >= 0 ? reinterpret_cast<const float4*>(P.G + (long long)p.gidx * P.ldg) + half * NV : nullptr;
+        uint32_t buf[2][CW];
+        float4 gb[NV];
+        tmem_ldN_issue(lane_taddr + d * 256 + half * CW, buf[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gb[j] = grow ? __ldg(grow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NV; ++j) gb[j] = grow ? __ldg(grow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
-          tmem_ld32_wait(buf[sl & 1]);
-          if (sl + 1 < 4) tmem_ld32_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * 32, buf[(sl + 1) & 1]);
-          const int c0 = sl * 64 + half * 32;
+          tmem_ldN_wait(buf[sl & 1]);
+          if (sl + 1 < 4) tmem_ldN_issue(lane_taddr + d * 256 + (sl + 1) * 64 + half * CW, buf[(sl + 1) & 1]);
+          const int c0 = sl * 64 + half * CW;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {               // bias adds on pairs; the logit sum keeps its sequential order
+          for (int j = 0; j < NV; ++j) {               // bias adds on pairs; the logit sum keeps its sequential order
             const float4 g = gb[j];
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
             float h0, h1, h2, h3;
@@ -136,7 +142,7 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
           }
           if (sl + 1 < 4) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gb[j] = grow ? __ldg(grow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NV; ++j) gb[j] = grow ? __ldg(grow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if (grow && half == 0) logit += __ldg(P.G + (long long)p.gidx * P.ldg + HID);
@@ -146,8 +152,10 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
       float a;
       {
         s.xchg[half * ROWS + row] = logit;
-        epi_sync<NEPI>();
-        const float l = __fdiv_rn(s.xchg[row] + s.xchg[ROWS + row], P.softmax_scale);
+        epi_sync<128 * PARTS>();
+        const float lsum = PARTS == 2 ? s.xchg[row] + s.xchg[ROWS + row]
+                                      : (s.xchg[row] + s.xchg[ROWS + row]) + (s.xchg[2 * ROWS + row] + s.xchg[3 * ROWS + row]);
+        const float l = __fdiv_rn(lsum, P.softmax_scale);
         float mx = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         const float ex = expf(l - mx);
@@ -158,9 +166,9 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
 
       if (threadIdx.x == EPI_T0) TC_TRACE(3004);       // softmax done
       // ---- value chain (layer 1 was built above) ----------------------------------------------------
-      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 13 * HID);
-      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 14 * HID);
-      epi_hidden<false, 2>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
+      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 13 * HID);
+      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 14 * HID);
+      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
 
       // geometry of this row's latent code for the value gather
       int py = 0, px = 0;
@@ -181,8 +189,8 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
         if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
         return __ldg(reinterpret_cast<const float4*>(fbase + (dy * W + dx) * C + ch));
       };
-      // 8 float4 = the 32 values of chunk [cp0, cp0+32)
-      auto load_values = [&](int cp0, float4 (&vb)[8]) {
+      // NV float4 = the CW values of chunk [cp0, cp0+CW)
+      auto load_values = [&](int cp0, float4 (&vb)[NV]) {
         if (tap32) {
           const float* src = nullptr;
           if (fbase != nullptr && cp0 < P.Dv) {
@@ -194,37 +202,37 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
             }
           }
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
+          for (int g = 0; g < NV; ++g)
             vb[g] = src ? __ldg(reinterpret_cast<const float4*>(src) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) vb[g] = value4(cp0 + 4 * g);
+          for (int g = 0; g < NV; ++g) vb[g] = value4(cp0 + 4 * g);
         }
       };
       const long long q = x_row0 + (row >> 2);    // row of x for this (query, neighbour) row's query
-      const int sub = (lane & 1) * 16 + ((lane >> 1) & 1) * 8;   // columns of a 32-chunk this lane ends up owning
+      const int sub = (lane & 1) * (CW / 2) + ((lane >> 1) & 1) * (CW / 4);   // columns of a chunk this lane ends up owning
       for (int c = 0; c < nchunks5; ++c) {
         const int units = min(2, P.units5 - 2 * c);
-        const int nsub = units * 2;                            // 32-column chunks per thread (alternating halves)
+        const int nsub = units * 2;                            // chunks per thread (interleaved with the other parts')
         uint32_t d = 0;
-        uint32_t buf[2][32];
-        float4 vb[8];
-        load_values(c * 256 + half * 32, vb);
+        uint32_t buf[2][CW];
+        float4 vb[NV];
+        load_values(c * 256 + half * CW, vb);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k >= nsub) break;                                // nsub is 2 or 4, warp-uniform
-          const int cc = 2 * k + half;
-          const int cp0 = c * 256 + cc * 32;
-          float v[32];
+          const int cc = PARTS * k + half;
+          const int cp0 = c * 256 + cc * CW;
+          float v[CW];
           if ((k & 1) == 0) {                                  // first chunk of an accumulator half
             d = epi_wait_half(s, e, k >> 1);
-            tmem_ld32_issue(lane_taddr + d * 256 + cc * 32, buf[k & 1]);
+            tmem_ldN_issue(lane_taddr + d * 256 + cc * CW, buf[k & 1]);
           }
-          tmem_ld32_wait(buf[k & 1]);
-          if ((k & 1) == 0) tmem_ld32_issue(lane_taddr + d * 256 + (cc + 2) * 32, buf[(k + 1) & 1]);
+          tmem_ldN_wait(buf[k & 1]);
+          if ((k & 1) == 0) tmem_ldN_issue(lane_taddr + d * 256 + (cc + PARTS) * CW, buf[(k + 1) & 1]);
           const uint64_t aa = pack2(a, a);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {               // (a * value) * (acc + bias), two columns per instruction
+          for (int g = 0; g < NV; ++g) {               // (a * value) * (acc + bias), two columns per instruction
             const float4 val = vb[g];
             const int o = cp0 + 4 * g;
             const float4 b4 = *reinterpret_cast<const float4*>(bv5 + o);
@@ -238,26 +246,33 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
                     v[4 * g + 2], v[4 * g + 3]);
           }
           if (k + 1 < nsub) load_values(cp0 + 64, vb);
-          // sum over the 4 neighbour rows (lanes 4q..4q+3), leaving each lane with 8 of the 32 columns
-          float r16[16], r8[8];
+          // sum over the 4 neighbour rows (lanes 4q..4q+3), leaving each lane with CW/4 of the chunk's columns
+          float r16[CW / 2], r8[CW / 4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float keep = (lane & 1) ? v[16 + i] : v[i];
-            const float send = (lane & 1) ? v[i] : v[16 + i];
+          for (int i = 0; i < CW / 2; ++i) {
+            const float keep = (lane & 1) ? v[CW / 2 + i] : v[i];
+            const float send = (lane & 1) ? v[i] : v[CW / 2 + i];
             r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float keep = (lane & 2) ? r16[8 + i] : r16[i];
-            const float send = (lane & 2) ? r16[i] : r16[8 + i];
+          for (int i = 0; i < CW / 4; ++i) {
+            const float keep = (lane & 2) ? r16[CW / 4 + i] : r16[i];
+            const float send = (lane & 2) ? r16[i] : r16[CW / 4 + i];
             r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
           }
-          if (valid) {                                         // 8 columns = one 16-byte store per half
-            uint4 h, l;
-            split2(r8[0], r8[1], h.x, l.x); split2(r8[2], r8[3], h.y, l.y);
-            split2(r8[4], r8[5], h.z, l.z); split2(r8[6], r8[7], h.w, l.w);
-            *reinterpret_cast<uint4*>(P.x_hi + q * P.Dvp + cp0 + sub) = h;
-            *reinterpret_cast<uint4*>(P.x_lo + q * P.Dvp + cp0 + sub) = l;
+          if (valid) {                                         // one 16-byte (8-byte when PARTS = 4) store per half
+            if constexpr (PARTS == 2) {
+              uint4 h, l;
+              split2(r8[0], r8[1], h.x, l.x); split2(r8[2], r8[3], h.y, l.y);
+              split2(r8[4], r8[5], h.z, l.z); split2(r8[6], r8[7], h.w, l.w);
+              *reinterpret_cast<uint4*>(P.x_hi + q * P.Dvp + cp0 + sub) = h;
+              *reinterpret_cast<uint4*>(P.x_lo + q * P.Dvp + cp0 + sub) = l;
+            } else {
+              uint2 h, l;
+              split2(r8[0], r8[1], h.x, l.x); split2(r8[2], r8[3], h.y, l.y);
+              *reinterpret_cast<uint2*>(P.x_hi + q * P.Dvp + cp0 + sub) = h;
+              *reinterpret_cast<uint2*>(P.x_lo + q * P.Dvp + cp0 + sub) = l;
+            }
           }
         }
         epi_release_d(s, e);
@@ -308,7 +323,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
     const float* bv5 = s.consts + 16 * HID;
     for (int it = 0; it < P.iters; ++it) {
       const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
-      pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
+      pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
     }
   }
 #ifdef CIAOSR_TC_TIMING
@@ -321,13 +336,21 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
 // CTA-pair variant (cta_group::2, tc_pipeline.cuh "CTA-pair mode"): the two CTAs of a cluster work on 256 consecutive rows
 // with ONE M = 256 UMMA stream issued by the leader; each CTA stages half of every weight operand.  Row-thread work is
 // the same function as above (its barrier arrivals go to the leader through TcShared::pair_rank).
-__global__ void __launch_bounds__(HEAD_THREADS, 1)
+// PARTS = row threads per row: 2 (384 threads) or 4 (640 threads: 16 row warps, four per SM sub-partition -- the row
+// threads are the critical path of this kernel and latency-bound at two warps per sub-partition).
+// NSPLIT: the N-split issue schedule of tc_pipeline.cuh (two N = 128 column halves per layer, epilogue of the first
+// half under the UMMAs of the second) instead of one N = 256 stream per layer.
+template <int PARTS, bool NSPLIT>
+__global__ void __launch_bounds__(128 + 128 * PARTS, 1)
 pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   TcShared s = tc_carve(smem);
   s.pair_rank = (int)cluster_ctarank();
-  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
-  const uint32_t tmem_base = tc_prologue_pair<NEPI>(s, smem);
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += 128 + 128 * PARTS) s.consts[i] = P.consts[i];
+#ifdef CIAOSR_TC_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
+#endif
+  const uint32_t tmem_base = tc_prologue_pair<128 * PARTS>(s, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks5 = (P.units5 + 1) / 2;
   const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
@@ -337,10 +360,15 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
     if (lane == 0) tma_prefetch_desc(&wmap);
     for (int it = 0; it < P.iters; ++it) {
       long long r = 0;                                   // 128-byte row of the blob
-      for (int j = 0; j < 6; ++j) { produce_job_pair(s, ps, &wmap, r, 4, 2); r += 4 * 2 * 2 * ROWS; }
+      for (int j = 0; j < 6; ++j) {
+        if (NSPLIT) produce_job_pair_split(s, ps, &wmap, r, 2);
+        else produce_job_pair(s, ps, &wmap, r, 4, 2);
+        r += 4 * 2 * 2 * ROWS;
+      }
       for (int c = 0; c < nchunks5; ++c) {
         const int units = min(2, P.units5 - 2 * c);
-        produce_job_pair(s, ps, &wmap, r, 4, units);
+        if (NSPLIT) produce_job_pair_split(s, ps, &wmap, r, units);
+        else produce_job_pair(s, ps, &wmap, r, 4, units);
         r += 4 * units * 2 * ROWS;
       }
     }
@@ -348,8 +376,14 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
     if (s.pair_rank == 0) {
       MmaState m{0, 0, 0};
       for (int it = 0; it < P.iters; ++it) {
-        for (int j = 0; j < 6; ++j) mma_job_pair(s, tmem_base, m, 4, 2, true);
-        for (int c = 0; c < nchunks5; ++c) mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+        for (int j = 0; j < 6; ++j) {
+          if (NSPLIT) mma_job_pair_split(s, tmem_base, m, 2, true);
+          else mma_job_pair(s, tmem_base, m, 4, 2, true);
+        }
+        for (int c = 0; c < nchunks5; ++c) {
+          if (NSPLIT) mma_job_pair_split(s, tmem_base, m, min(2, P.units5 - 2 * c), c == 0);
+          else mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -361,9 +395,13 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
     const float* bv5 = s.consts + 16 * HID;
     for (int it = 0; it < P.iters; ++it) {
       const long long tile = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;
-      pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
+      pair_tile_rows<PARTS>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
     }
   }
+#ifdef CIAOSR_TC_TIMING
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = 0;
+#endif
   tc_teardown_pair(tmem_base);
 }
 
@@ -584,7 +622,7 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
     for (int it = 0; it < Q.iters; ++it) {
       const long long st = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;      // super-tile = 128 queries
       for (int sub = 0; sub < 4; ++sub)
-        pair_tile_rows(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4));
+        pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4));
       // publish x: global stores (generic proxy) -> visible device-wide -> visible to the TMA engine (async proxy)
       __threadfence();
       asm volatile("fence.proxy.async.global;" ::: "memory");

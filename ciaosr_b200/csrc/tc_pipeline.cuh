@@ -336,12 +336,16 @@ __device__ __forceinline__ void produce_job_pair(const TcShared& s, ProdState& p
       ps.bits ^= 1u << stage;
       if (leader_lane) {
         const uint32_t full = bar_at(s, w_full_bar(stage));
+        if (TC_DBG(2)) {
+          if (rank == 0) mbar_arrive(full);
+        } else {
         if (rank == 0) mbar_arrive_expect_tx(full, 2 * bytes);
         const long long r = row0 + ((long long)(sl * units + (units == 2 ? rank : 0)) * 2 + lo) * ROWS +
                             (units == 2 ? 0 : 64 * rank);
         const uint32_t dst = s.w + stage * SLAB_BYTES;
         tma_load_2d_cg2(dst, wmap, 0, (int)r, full);
         if (units == 2) tma_load_2d_cg2(dst + SLAB_BYTES / 2, wmap, 0, (int)r + 64, full);
+        }
       }
       __syncwarp();
     }
@@ -350,7 +354,7 @@ __device__ __forceinline__ void produce_job_pair(const TcShared& s, ProdState& p
 }
 
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
-#ifdef CIAOSR_TC_TIMING
+#if defined(CIAOSR_TC_TIMING) && !defined(CIAOSR_TC_TRACE_ONLY)
   const long long tt = clock64();
   struct Rec { int tag; long long t; __device__ ~Rec() { tc_time_add(tag / 10, t); } } rec{tag, tt};
 #endif
@@ -382,6 +386,7 @@ __device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_ba
       mbar_wait(bar_at(s, BAR_A_READY + slot), (m.aready_bits >> slot) & 1, 210 + slot);
       m.aready_bits ^= 1u << slot;
     }
+    TC_TRACE(1000 + sl);          // issuer: operand slab sl available
     const uint32_t a_hi = desc_lo(s.a_hi + slot * SLAB_BYTES), a_lo = desc_lo(s.a_lo + slot * SLAB_BYTES);
     const uint32_t b_hi = desc_lo(s.w + sp * SLAB_BYTES), b_lo = desc_lo(s.w + (sp + 1) * SLAB_BYTES);
     mbar_wait(bar_at(s, w_full_bar(sp)), (m.wbits >> sp) & 1, 220);
@@ -413,6 +418,90 @@ __device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_ba
     if (units == 2) umma_commit_cg2(bar_at(s, BAR_D_READY + 2 * d + 1), 3);
   }
   __syncwarp();
+  TC_TRACE(1010);                 // issuer: job fully issued
+  ++m.jobctr;
+}
+
+// ---- CTA-pair mode, N-split schedule ------------------------------------------------------------------------------
+// Measured (tools/ubench/mma_bench.cu, r02x): a dependent chain of N = 256 UMMAs runs at the full 128 cycles each (M = 128
+// per CTA), N <= 128 at a 74-cycle issue floor, and switching accumulators between consecutive UMMAs costs a ~180-cycle
+// drain.  In the kernels the N = 256 UMMAs took 169 cycles (shared-memory bandwidth: operand reads + weight writes +
+// the row threads' operand stores), and -- worse -- a layer's epilogue could not start before ALL of its UMMAs were done
+// (one N = 256 instruction covers both accumulator halves), so a third of every layer's period had an idle tensor pipe
+// (r02w trace: 3.0 k cycles of row work exposed + 0.9 k of latencies per 12.0 k).  Here every layer is issued as two
+// N = 128 column halves H0, H1 over two K-slab groups, in the order
+//     (H0: s0 s1) (H1: s0 s1) (H0: s2 s3) -> commit D_READY[H0]     (H1: s2 s3) -> commit D_READY[H1]
+// so that the row threads convert H0 (= the next layer's K-slabs 0, 1) while the UMMAs of (H1: s2 s3) run, and the next
+// layer's first four units only need those two slabs: the tensor pipe has work throughout.  Accumulators are switched 4
+// times per layer.  One ring stage = one (K-slab, column half) unit of this CTA: [W_hi 64 rows | W_lo 64 rows] = 16 KB.
+__device__ __forceinline__ void produce_job_pair_split(const TcShared& s, ProdState& ps, const CUtensorMap* wmap,
+                                                       long long row0, int units) {
+  const bool leader_lane = (threadIdx.x & 31) == 0;
+  const int rank = s.pair_rank;
+  for (int g = 0; g < 2; ++g)
+    for (int h = 0; h < units; ++h)
+      for (int sl = 2 * g; sl < 2 * g + 2; ++sl) {
+        const int stage = (int)(ps.slabs & 3);
+        mbar_wait(bar_at(s, w_empty_bar(stage)), ((ps.bits >> stage) & 1) ^ 1, 100 + stage);
+        ps.bits ^= 1u << stage;
+        if (leader_lane) {
+          const uint32_t full = bar_at(s, w_full_bar(stage));
+          if (TC_DBG(2)) {
+            if (rank == 0) mbar_arrive(full);
+          } else {
+          if (rank == 0) mbar_arrive_expect_tx(full, 2 * SLAB_BYTES);          // both CTAs' [hi | lo] halves
+          const long long r = row0 + ((long long)(sl * units + h) * 2) * ROWS + 64 * rank;
+          const uint32_t dst = s.w + stage * SLAB_BYTES;
+          tma_load_2d_cg2(dst, wmap, 0, (int)r, full);                         // W_hi rows [64 rank, 64 rank + 64) of the unit
+          tma_load_2d_cg2(dst + SLAB_BYTES / 2, wmap, 0, (int)r + ROWS, full); // W_lo, same rows
+          }
+        }
+        __syncwarp();
+        ++ps.slabs;
+      }
+}
+
+__device__ __forceinline__ void mma_job_pair_split(const TcShared& s, uint32_t tmem_base, MmaState& m, int units,
+                                                   bool a_new) {
+  // Issue-side overheads matter at N = 128 (74-cycle issue floor per UMMA, r02z mma_pattern: every tcgen05.commit costs
+  // ~76 cycles of tensor time and every wait + tcgen05.fence ~66), so this path commits once per unit (W_EMPTY; A_FREE is
+  // never waited on by the pair kernel and D_READY is per half) and fences only after D_FREE -- operand visibility comes
+  // from the mbarrier (TMA complete_tx / fence.proxy.async + arrive), not from a tcgen05 fence.
+  const bool leader = (threadIdx.x & 31) == 0;
+  const uint32_t idesc = make_idesc_split(2 * ROWS, UNIT_N);
+  const uint32_t d = m.jobctr & 1, n = m.jobctr >> 1;
+  mbar_wait(bar_at(s, BAR_D_FREE + d), (n + 1) & 1, 200);
+  tc_fence_after();
+  for (int g = 0; g < 2; ++g)
+    for (int h = 0; h < units; ++h) {
+      const uint32_t dcol = tmem_base + d * 256 + h * UNIT_N;
+      for (int sl = 2 * g; sl < 2 * g + 2; ++sl) {
+        if (a_new && h == 0) {
+          mbar_wait(bar_at(s, BAR_A_READY + sl), (m.aready_bits >> sl) & 1, 210 + sl);
+          m.aready_bits ^= 1u << sl;
+          TC_TRACE(1000 + sl);          // issuer: operand slab sl available
+        }
+        const int stage = (int)(m.slabs & 3);
+        const uint32_t a_hi = desc_lo(s.a_hi + sl * SLAB_BYTES), a_lo = desc_lo(s.a_lo + sl * SLAB_BYTES);
+        const uint32_t b_hi = desc_lo(s.w + stage * SLAB_BYTES), b_lo = desc_lo(s.w + stage * SLAB_BYTES + SLAB_BYTES / 2);
+        mbar_wait(bar_at(s, w_full_bar(stage)), (m.wbits >> stage) & 1, 220);
+        m.wbits ^= 1u << stage;
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_cg2(dcol, a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, (sl | ks) != 0 ? 1u : 0u);
+            umma_cg2(dcol, a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_cg2(dcol, a_hi + 2 * ks, b_lo + 2 * ks, DESC_HI, idesc, 1u);
+          umma_commit_cg2(bar_at(s, w_empty_bar(stage)), 3);
+          if (g == 1 && sl == 3) umma_commit_cg2(bar_at(s, BAR_D_READY + 2 * d + h), 3);
+        }
+        __syncwarp();
+        ++m.slabs;
+      }
+    }
+  TC_TRACE(1010);                 // issuer: job fully issued
   ++m.jobctr;
 }
 
@@ -473,32 +562,34 @@ __device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
   ++e.jobctr;
 }
 
-// Hidden-layer epilogue: next A = relu(D + bias).  HALVES = 1: this thread converts all 64 columns of
-// every slab; HALVES = 2: only columns [32*half, 32*half + 32).  Columns 0..127 are converted as soon as
-// the first accumulator half is complete (the UMMAs of the second half are still running).
+// Hidden-layer epilogue: next A = relu(D + bias).  HALVES = threads per row: 1: this thread converts all 64 columns of
+// every slab; 2: columns [32*half, 32*half + 32); 4: columns [16*half, 16*half + 16) (`half` is then the quarter index).
+// Columns 0..127 are converted as soon as the first accumulator half is complete.
 // (not inlined: it is instantiated once and called per layer -- the fully unrolled body is ~400
 // instructions, and inlining it 5x per tile made instruction fetch 17 % of the row warps' stall time)
 template <bool WAIT_FREE, int HALVES>
 __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t lane_taddr, int row, int half,
                                            const float* __restrict__ bias_s) {
-  constexpr int NCH = 4 * (2 / HALVES);          // 32-column chunks this thread handles
+  constexpr int CW = HALVES == 4 ? 16 : 32;      // columns per chunk
+  constexpr int NCH = HID / (CW * HALVES);       // chunks this thread handles
   constexpr int PER_HALF = NCH / 2;
-  uint32_t buf[2][32];
-  auto col_of = [&](int c) { return HALVES == 2 ? (c * 64 + half * 32) : (c * 32); };
+  uint32_t buf[2][CW];
+  auto col_of = [&](int c) { return HALVES == 1 ? (c * 32) : (c * 64 + half * CW); };
   uint32_t d = 0;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     if (c % PER_HALF == 0) {                     // first chunk of an accumulator half
       d = epi_wait_half(s, e, c / PER_HALF);
-      tmem_ld32_issue(lane_taddr + d * 256 + col_of(c), buf[c & 1]);
+      tmem_ldN_issue(lane_taddr + d * 256 + col_of(c), buf[c & 1]);
     }
-    tmem_ld32_wait(buf[c & 1]);
-    if ((c + 1) % PER_HALF != 0) tmem_ld32_issue(lane_taddr + d * 256 + col_of(c + 1), buf[(c + 1) & 1]);
+    tmem_ldN_wait(buf[c & 1]);
+    if ((c + 1) % PER_HALF != 0) tmem_ldN_issue(lane_taddr + d * 256 + col_of(c + 1), buf[(c + 1) & 1]);
     const int col = col_of(c), sl = col >> 6;
-    if (HALVES == 2 || (c & 1) == 0) slab_begin(s, e, sl, WAIT_FREE);
-    float v[32];
+    if (HALVES >= 2 || (c & 1) == 0) slab_begin(s, e, sl, WAIT_FREE);
+    float v[CW];
+    if (!TC_DBG(1)) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < CW / 4; ++j) {
       const float4 b4 = reinterpret_cast<const float4*>(bias_s + col)[j];
       float t0, t1, t2, t3;                      // bias add on pairs (FADD2), ReLU per element
       unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j]), __uint_as_float(buf[c & 1][4 * j + 1])), pack2(b4.x, b4.y)), t0, t1);
@@ -508,14 +599,18 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
       v[4 * j + 2] = fmaxf(t2, 0.0f);
       v[4 * j + 3] = fmaxf(t3, 0.0f);
     }
-    a_store32(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
-    if (HALVES == 2) {
+    a_storeN(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
+    }
+    if (HALVES >= 2) {
       // single-CTA mode: per slab -- the next layer's first UMMAs start one slab earlier (-3 % kernel time).  CTA-pair
       // mode: the M = 256 UMMAs are ~3x cheaper per row and the ROW threads are the critical path (r02n: issuer idle
       // 63 %), so they publish two slabs per fence.proxy.async (the most expensive step of this epilogue) instead.
-      if (s.pair_rank < 0) slab_done(s, sl);
+      // [r03] ... except the FIRST slabs: the issuer idles until slab 0 arrives (r02w trace: 3.0 k of every 12.0 k-cycle
+      // layer period), so slabs 0 and 1 are published one by one and only 2 + 3 share a fence.
+      if (s.pair_rank < 0 || sl < 2) slab_done(s, sl);
       else if (c & 1) slabs_done2(s, sl - 1, sl);
     } else if (c & 1) slab_done(s, sl);
+    if (threadIdx.x == EPI_T0) TC_TRACE(2020 + sl);    // rows: this warp's part of slab sl written (published if odd / single mode)
   }
   epi_release_d(s, e);
 }

@@ -847,3 +847,16 @@ def test_cta_pair_umma_path_matches_default(monkeypatch):
         torch.cuda.synchronize()
         print(f"CTA-pair UMMA path {b}x{h}x{w} x{s}: max-abs vs single-CTA path {max_abs(out, ref):.2e}")
         assert max_abs(out, ref) < 1e-6
+        # opt-in schedules of the pair kernel.  N-split: same products in the same order per output element -> identical;
+        # four row threads per row: a row's logit is the sum of four partial sums instead of two -> fp32 re-association only
+        monkeypatch.setenv("CIAOSR_HEAD_NSPLIT", "1")
+        outn = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        monkeypatch.setenv("CIAOSR_HEAD_ROWPARTS", "4")
+        out4n = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        monkeypatch.delenv("CIAOSR_HEAD_NSPLIT", raising=False)
+        out4 = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        monkeypatch.delenv("CIAOSR_HEAD_ROWPARTS", raising=False)
+        torch.cuda.synchronize()
+        print(f"  N-split schedule: max-abs vs default {max_abs(outn, out):.2e}; four row threads per row: {max_abs(out4, out):.2e}")
+        assert torch.equal(outn, out) and torch.equal(out4n, out4)
+        assert max_abs(out4, out) < 5e-6

@@ -11,6 +11,8 @@ lq, coord, cell = bench.make_inputs(bench.B, 100)
 lq = (lq - torch.tensor(bench.RGB_MEAN).view(1, 3, 1, 1)).to(dev)
 coord, cell = coord.to(dev), cell.to(dev)
 lib = _lib.load()
+if os.environ.get("CIAOSR_DBG_FLAGS"):
+    lib.ciaosr_debug_flags(int(os.environ["CIAOSR_DBG_FLAGS"]))
 buf = (ctypes.c_ulonglong * (2 * 8192))(); n = ctypes.c_uint(0)
 with torch.no_grad():
     for _ in range(2):
@@ -24,5 +26,6 @@ t0 = ev[0][0]
 NAMES = {1010: "ISSUER job issued", 2010: "rows  D drained", 3000: "rows  TILE START", 3001: "rows  k.L1 written",
          3002: "rows  k.L4 complete", 3003: "rows  v.L1 written", 3004: "rows  softmax done"}
 for t, tag in ev:
-    name = NAMES.get(tag) or (f"ISSUER slab {tag - 1000} ready" if 1000 <= tag < 1010 else f"rows  D half {tag - 2000} ready")
+    name = NAMES.get(tag) or (f"ISSUER slab {tag - 1000} ready" if 1000 <= tag < 1010 else
+                              f"rows  slab {tag - 2020} written" if 2020 <= tag < 2030 else f"rows  D half {tag - 2000} ready")
     print(f"{t - t0:10d}  {name}")

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int nd, long l
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const uint32_t ks = j & 3, sl = j >> 2;
-        mma<CG, ATMEM>(tb + (nd > 1 ? (uint32_t)(j & 1) * 128u : 0u), a0 + sl * astep_sl + ks * astep_ks,
+        mma<CG, ATMEM>(tb + (nd > 1 ? (uint32_t)(j % nd) * (uint32_t)(ATMEM ? 128 : N) : 0u), a0 + sl * astep_sl + ks * astep_ks,
                        b0 + sl * (16384 >> 4) + ks * 2, idesc, (i | j) >= nd ? 1u : 0u);
         if (commit_every && ((j + 1) % commit_every) == 0) {
           if (CG == 1) umma_commit(smem_u32(&bar2[(j / commit_every) & 3]));
@@ -143,5 +143,14 @@ int main() {
   run<1, true>("LONG cta_group::1 A=tmem", 128, 1, 4096 * 2000);
   run<1, false>("cta_group::1 A=smem alt-D", 128, 2);
   run<1, false>("cta_group::1 A=smem alt-D", 64, 4);
+  run<1, false>("cta_group::1 A=smem alt-D", 256, 2);
+  run<1, false>("cta_group::1 A=smem alt-D", 128, 4);
+  run<1, true>("cta_group::1 A=tmem alt-D", 128, 2);
+  run<2, false>("cta_group::2 A=smem alt-D", 256, 2);
+  run<2, false>("cta_group::2 A=smem alt-D", 128, 2);
+  run<2, false>("cta_group::2 A=smem alt-D", 128, 4);
+  run<2, false>("cta_group::2 A=smem alt-D", 64, 4);
+  for (int N : {32, 64, 96, 128, 160, 192, 224, 256}) run<2, false>("cta_group::2 A=smem sweep", N, 1);
+  for (int N : {32, 64, 96, 128, 192, 256}) run<1, false>("cta_group::1 A=smem sweep", N, 1);
   return 0;
 }
