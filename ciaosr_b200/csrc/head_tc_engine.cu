@@ -328,6 +328,10 @@ static int tc_grid(int n_tiles, int CL) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* e = getenv("CIAOSR_DBG_MAXSMS")) {          // experiment: fewer persistent CTAs (power / shared-resource probe)
+    const int m = atoi(e);
+    if (m > 0 && m < sms) sms = m;
+  }
   sms = sms / CL * CL;
   const int want = (n_tiles + CL - 1) / CL * CL;
   return want < sms ? want : sms;

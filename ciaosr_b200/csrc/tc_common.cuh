@@ -369,6 +369,9 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h1), "f"(v0 - h0));
 }
+__device__ __forceinline__ void split2_relu(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  split2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f), hi, lo);
+}
 __host__ __device__ inline void split_scalar(float w, split_t& hi, split_t& lo) {
   hi = __float2bfloat16_rn(w);
   lo = __float2bfloat16_rn(w - __bfloat162float(hi));
@@ -381,6 +384,18 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   unpack2(sub2(pack2(v0, v1), pack2(h.x, h.y)), d0, d1);          // one FADD2 for both residuals
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 }
+// split of relu(v): the ReLU rides on the conversions (cvt ... .relu clamps negative results to +0), which removes one
+// FMNMX per element from the row threads (they are bound by the half-rate ALU / conversion pipes, r02w).  hi is rounded
+// TOWARD ZERO so that the residual of a positive value is never negative (a .relu on the second conversion would
+// otherwise clip it): |v - hi| < ulp_fp16(v) instead of <= ulp/2, i.e. the pair carries >= 21 instead of 22 mantissa
+// bits; negative v gives hi = 0, residual v, lo = relu(v) = 0.
+__device__ __forceinline__ void split2_relu(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  float d0, d1;
+  unpack2(sub2(pack2(v0, v1), pack2(h.x, h.y)), d0, d1);
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+}
 __device__ inline void split_scalar(float w, split_t& hi, split_t& lo) {
   hi = __float2half_rn(fminf(fmaxf(w, -65504.0f), 65504.0f));
   lo = __float2half_rn(fminf(fmaxf(w - __half2float(hi), -65504.0f), 65504.0f));
@@ -389,7 +404,7 @@ __device__ inline void split_scalar(float w, split_t& hi, split_t& lo) {
 
 // Write 32 consecutive K-columns [c0, c0+32) (c0 % 32 == 0, within one 64-wide slab) of
 // operand row `row` into the hi and lo slabs (SW128: 16-byte chunk j of a row lives at j ^ (row & 7)).
-template <class T>
+template <bool RELU = false, class T>
 __device__ __forceinline__ void a_store32(uint32_t slab_hi, uint32_t slab_lo, int row, int c0,
                                           const T (&v)[32]) {
   const uint32_t rbase = (uint32_t)row * 128u;
@@ -397,7 +412,10 @@ __device__ __forceinline__ void a_store32(uint32_t slab_hi, uint32_t slab_lo, in
   for (int j = 0; j < 4; ++j) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split2(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+    for (int i = 0; i < 4; ++i) {
+      if (RELU) split2_relu(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+      else split2(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+    }
     const uint32_t chunk = (uint32_t)(((c0 >> 3) + j) ^ (row & 7)) << 4;
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_hi + rbase + chunk), "r"(h[0]),
                  "r"(h[1]), "r"(h[2]), "r"(h[3])
@@ -409,7 +427,7 @@ __device__ __forceinline__ void a_store32(uint32_t slab_hi, uint32_t slab_lo, in
 }
 
 // 16 consecutive K-columns [c0, c0+16) (c0 % 16 == 0): two 16-byte chunks per half
-template <class T>
+template <bool RELU = false, class T>
 __device__ __forceinline__ void a_store16(uint32_t slab_hi, uint32_t slab_lo, int row, int c0,
                                           const T (&v)[16]) {
   const uint32_t rbase = (uint32_t)row * 128u;
@@ -417,7 +435,10 @@ __device__ __forceinline__ void a_store16(uint32_t slab_hi, uint32_t slab_lo, in
   for (int j = 0; j < 2; ++j) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split2(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+    for (int i = 0; i < 4; ++i) {
+      if (RELU) split2_relu(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+      else split2(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1], h[i], l[i]);
+    }
     const uint32_t chunk = (uint32_t)(((c0 >> 3) + j) ^ (row & 7)) << 4;
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_hi + rbase + chunk), "r"(h[0]),
                  "r"(h[1]), "r"(h[2]), "r"(h[3])
@@ -427,10 +448,10 @@ __device__ __forceinline__ void a_store16(uint32_t slab_hi, uint32_t slab_lo, in
                  : "memory");
   }
 }
-template <class T>
-__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[32]) { a_store32(hi, lo, row, c0, v); }
-template <class T>
-__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[16]) { a_store16(hi, lo, row, c0, v); }
+template <bool RELU = false, class T>
+__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[32]) { a_store32<RELU>(hi, lo, row, c0, v); }
+template <bool RELU = false, class T>
+__device__ __forceinline__ void a_storeN(uint32_t hi, uint32_t lo, int row, int c0, const T (&v)[16]) { a_store16<RELU>(hi, lo, row, c0, v); }
 
 // byte offset of element (n, k) inside a [128 x 64] SW128 slab (used by the weight packer)
 __host__ __device__ inline uint32_t sw128_offset(int n, int k) {

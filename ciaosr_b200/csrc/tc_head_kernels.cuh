@@ -36,10 +36,16 @@ struct PairParams {
 
 // layer 1 of imnet_k / imnet_v from the LR hoist:  relu(P[pix] + b1 + rc . [rel_y, rel_x, sc_y, sc_x])
 // PARTS = row threads per row (2 or 4); `half` = this thread's part: columns [CW*half, CW*half + CW) of every slab
-template <int PARTS>
-__device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
-                                           const float* __restrict__ P, const float* __restrict__ rc_s,
-                                           const float* __restrict__ b1_s) {
+// WAITK (the value chain's layer 1): the operand slots still hold k.L4's input until its UMMAs are complete, so the
+// gather and the arithmetic of slab 0 run first and the wait for k.L4's accumulator sits right before the first store:
+// the issuer sees slab 0 ~2 k cycles earlier than with the wait in front.  Returns k.L4's accumulator index.
+// WAITK = 2 (the NEXT tile's key layer 1, written before this tile's last value chunk is reduced): same, the wait is for
+// the last accumulator of this tile (`wait_halves` column halves).
+template <int PARTS, int WAITK>
+__device__ __noinline__ uint32_t gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
+                                               const float* __restrict__ P, const float* __restrict__ rc_s,
+                                               const float* __restrict__ b1_s, int wait_halves = 2) {
+  uint32_t dk = 0;
   constexpr int CW = 64 / PARTS, NV = CW / 4;
   const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * NV : nullptr;
   float4 buf[NV];
@@ -69,26 +75,41 @@ __device__ __noinline__ void gen_layer1(const TcShared& s, EpiState& e, int row,
       t = fma2(pack2(r1.x, r1.y), rx, t);
       t = fma2(pack2(r2.x, r2.y), sy, t);
       t = fma2(pack2(r3.x, r3.y), sx, t);
-      float t0, t1;
-      unpack2(t, t0, t1);
-      v[i] = fmaxf(t0, 0.0f);
-      v[i + 1] = fmaxf(t1, 0.0f);
+      unpack2(t, v[i], v[i + 1]);                      // the ReLU is part of the operand split (split2_relu)
+    }
+    if (WAITK && sl == 0) {
+      dk = epi_wait_half(s, e, 0);
+      if (wait_halves == 2) epi_wait_half(s, e, 1);
+      if (WAITK == 1 && threadIdx.x == EPI_T0) TC_TRACE(3002);       // k.L4 complete
     }
     slab_begin(s, e, sl, false);
-    if (!TC_DBG(1)) a_storeN(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * CW, v);
+    if (!TC_DBG(1)) a_storeN<true>(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, half * CW, v);
     if (s.pair_rank < 0 || sl < 2) slab_done(s, sl);     // CTA-pair mode: slabs 2 + 3 share a fence (see epi_hidden)
     else if (sl & 1) slabs_done2(s, sl - 1, sl);
   }
+  return dk;
 }
 
 // Row-thread work of ONE pair tile (128 (query, neighbour) rows = 32 queries): layer 1 of both chains from the LR hoists,
 // the hidden-layer epilogues, logits + softmax over the 4 neighbours, the value gather and the weighted sum -> x rows
 // [x_row0, x_row0 + 32) of P.x_hi / P.x_lo.  `cst` = the pair constants in shared memory, `bv5` = the padded last bias.
 // PARTS = row threads per row (2: 32-column chunks, 4: 16-column chunks); `half` = this thread's part index.
+// Software pipeline across tiles [r03]: `p` is this tile's pair geometry, computed during the PREVIOUS tile (compute_pair is
+// ~3.6 k cycles of dependent global loads and divisions); on return it holds the geometry of `next_tile` (< 0: none),
+// computed here while the value chain's UMMAs run.  Layer 1 of the next tile's key chain is written as soon as the last
+// UMMA of this tile is complete -- BEFORE the last value chunk is reduced -- so the tensor pipe works on the next tile
+// while this tile's x rows are finished (r02w trace: 12.7 k of every 104 k-cycle tile period had it idle at the boundary).
+__device__ __forceinline__ PairInfo pair_info_of(const PairParams& P, long long tile, int row) {
+  const long long R = tile * ROWS + row;
+  PairInfo p;
+  if (tile >= 0 && tile < P.n_tiles && R < P.total_rows) p = compute_pair(P.pc, P.coord, P.cell, R >> 2, (int)(R & 3));
+  else { p.pix = -1; p.gidx = -1; p.rel_y = p.rel_x = p.sc_y = p.sc_x = 0.0f; }
+  return p;
+}
 template <int PARTS>
 __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, const PairParams& P, const float* cst,
                                                const float* bv5, uint32_t lane_taddr, int row, int half, int lane,
-                                               long long tile, long long x_row0) {
+                                               long long tile, long long x_row0, PairInfo& p, bool first, long long next_tile) {
   const int C = P.C, H = P.pc.H, W = P.pc.W;
   constexpr int CW = 64 / PARTS, NV = CW / 4;    // columns / float4s per chunk
   const bool tap32 = (C % CW) == 0;              // a chunk never straddles a tap
@@ -96,22 +117,16 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
   {
       const long long R = tile * ROWS + row;
       const bool valid = tile < P.n_tiles && R < P.total_rows;
-      PairInfo p;
-      if (valid) p = compute_pair(P.pc, P.coord, P.cell, R >> 2, (int)(R & 3));
-      else { p.pix = -1; p.gidx = -1; p.rel_y = p.rel_x = p.sc_y = p.sc_x = 0.0f; }
 
       // ---- key chain -----------------------------------------------------------------------
       if (threadIdx.x == EPI_T0) TC_TRACE(3000);       // tile start
-      gen_layer1<PARTS>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);
+      if (first) gen_layer1<PARTS, 0>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);   // else: written by the previous tile
       if (threadIdx.x == EPI_T0) TC_TRACE(3001);       // k.L1 written
       epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 5 * HID);
       epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 6 * HID);
       // k.L4 is complete once both accumulator halves are; that also frees the operand slabs, so the value
       // chain's layer 1 is built FIRST: the UMMAs of v.L2 then run while the logits are reduced from D.
-      const uint32_t dk = epi_wait_half(s, e, 0);
-      epi_wait_half(s, e, 1);
-      if (threadIdx.x == EPI_T0) TC_TRACE(3002);       // k.L4 complete
-      gen_layer1<PARTS>(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      const uint32_t dk = gen_layer1<PARTS, 1>(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
       if (threadIdx.x == EPI_T0) TC_TRACE(3003);       // v.L1 written
       float logit = 0.0f;
       {
@@ -165,6 +180,9 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
       }
 
       if (threadIdx.x == EPI_T0) TC_TRACE(3004);       // softmax done
+      // everything below only needs pix of this tile's geometry; the next tile's is computed under the value chain's UMMAs
+      const int pix = p.pix;
+      p = pair_info_of(P, next_tile, row);
       // ---- value chain (layer 1 was built above) ----------------------------------------------------
       epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 13 * HID);
       epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 14 * HID);
@@ -174,11 +192,11 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
       int py = 0, px = 0;
       const float* fbase = nullptr;
       const float* nbase = nullptr;
-      if (p.pix >= 0) {
-        const int hw = p.pix % (H * W);
+      if (pix >= 0) {
+        const int hw = pix % (H * W);
         py = hw / W; px = hw % W;
-        fbase = P.featT + (long long)p.pix * C;
-        if (P.nlT) nbase = P.nlT + (long long)p.pix * P.Cn;
+        fbase = P.featT + (long long)pix * C;
+        if (P.nlT) nbase = P.nlT + (long long)pix * P.Cn;
       }
       // value[cp .. cp+3] in tap-major order (cp % 4 == 0); zeros outside the image / past Dv
       auto value4 = [&](int cp) -> float4 {
@@ -215,6 +233,10 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
         const int units = min(2, P.units5 - 2 * c);
         const int nsub = units * 2;                            // chunks per thread (interleaved with the other parts')
         uint32_t d = 0;
+        // last chunk: once its accumulator is complete every UMMA of this tile is, and the operand slots are free:
+        // the next tile's k.L1 goes in first, then this chunk is reduced while the tensor pipe runs the next tile's k.L2
+        const bool ahead = c == nchunks5 - 1 && next_tile >= 0;
+        if (ahead) d = gen_layer1<PARTS, 2>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID, units);
         uint32_t buf[2][CW];
         float4 vb[NV];
         load_values(c * 256 + half * CW, vb);
@@ -225,7 +247,7 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
           const int cp0 = c * 256 + cc * CW;
           float v[CW];
           if ((k & 1) == 0) {                                  // first chunk of an accumulator half
-            d = epi_wait_half(s, e, k >> 1);
+            if (!ahead) d = epi_wait_half(s, e, k >> 1);
             tmem_ldN_issue(lane_taddr + d * 256 + cc * CW, buf[k & 1]);
           }
           tmem_ldN_wait(buf[k & 1]);
@@ -321,9 +343,12 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
     EpiState e{0, 0, 0};
     const float* cst = s.consts;
     const float* bv5 = s.consts + 16 * HID;
+    auto tile_of = [&](int it) { return ((long long)it * n_clusters + cluster_id) * CL + cta_rank; };
+    PairInfo pinfo = pair_info_of(P, tile_of(0), row);
     for (int it = 0; it < P.iters; ++it) {
-      const long long tile = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;
-      pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
+      const long long tile = tile_of(it);
+      pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4), pinfo, it == 0,
+                        it + 1 < P.iters ? tile_of(it + 1) : -1);
     }
   }
 #ifdef CIAOSR_TC_TIMING
@@ -393,9 +418,12 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
     EpiState e{0, 0, 0};
     const float* cst = s.consts;
     const float* bv5 = s.consts + 16 * HID;
+    auto tile_of = [&](int it) { return ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank; };
+    PairInfo pinfo = pair_info_of(P, tile_of(0), row);
     for (int it = 0; it < P.iters; ++it) {
-      const long long tile = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;
-      pair_tile_rows<PARTS>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4));
+      const long long tile = tile_of(it);
+      pair_tile_rows<PARTS>(s, e, P, cst, bv5, lane_taddr, row, half, lane, tile, tile * (ROWS / 4), pinfo, it == 0,
+                            it + 1 < P.iters ? tile_of(it + 1) : -1);
     }
   }
 #ifdef CIAOSR_TC_TIMING
@@ -619,10 +647,15 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
     const float* cst = s.consts;
     const float* bv5 = s.consts + 16 * HID;
     const float* qcst = s.consts + qoff;
+    PairInfo pinfo;
     for (int it = 0; it < Q.iters; ++it) {
       const long long st = ((long long)it * n_clusters + cluster_id) * CL + cta_rank;      // super-tile = 128 queries
-      for (int sub = 0; sub < 4; ++sub)
-        pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4));
+      for (int sub = 0; sub < 4; ++sub) {
+        // pipelined across the four pair tiles of a super-tile; the query tile in between uses the operand slots
+        if (sub == 0) pinfo = pair_info_of(P, st * 4, row);
+        pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4), pinfo,
+                          sub == 0, sub < 3 ? st * 4 + sub + 1 : -1);
+      }
       // publish x: global stores (generic proxy) -> visible device-wide -> visible to the TMA engine (async proxy)
       __threadfence();
       asm volatile("fence.proxy.async.global;" ::: "memory");

@@ -591,15 +591,11 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) {
       const float4 b4 = reinterpret_cast<const float4*>(bias_s + col)[j];
-      float t0, t1, t2, t3;                      // bias add on pairs (FADD2), ReLU per element
-      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j]), __uint_as_float(buf[c & 1][4 * j + 1])), pack2(b4.x, b4.y)), t0, t1);
-      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j + 2]), __uint_as_float(buf[c & 1][4 * j + 3])), pack2(b4.z, b4.w)), t2, t3);
-      v[4 * j] = fmaxf(t0, 0.0f);
-      v[4 * j + 1] = fmaxf(t1, 0.0f);
-      v[4 * j + 2] = fmaxf(t2, 0.0f);
-      v[4 * j + 3] = fmaxf(t3, 0.0f);
+      // bias add on pairs (FADD2); the ReLU is part of the operand split (split2_relu)
+      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j]), __uint_as_float(buf[c & 1][4 * j + 1])), pack2(b4.x, b4.y)), v[4 * j], v[4 * j + 1]);
+      unpack2(add2(pack2(__uint_as_float(buf[c & 1][4 * j + 2]), __uint_as_float(buf[c & 1][4 * j + 3])), pack2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
     }
-    a_storeN(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
+    a_storeN<true>(s.a_hi + sl * SLAB_BYTES, s.a_lo + sl * SLAB_BYTES, row, col & 63, v);
     }
     if (HALVES >= 2) {
       // single-CTA mode: per slab -- the next layer's first UMMAs start one slab earlier (-3 % kernel time).  CTA-pair
