@@ -539,6 +539,11 @@ def main():
             gold = torch.from_numpy(np.load(gpath)["out"])
             parity["max_abs_vs_reference_golden"] = float((out_timed[:gold.shape[0]].cpu() - gold).abs().max())
             parity["golden"] = "tests/golden/full_cfg2.npz (crops 0-1, unmodified reference on CPU)"
+            mean = torch.tensor(RGB_MEAN, dtype=torch.float64)          # rgb_std = 1 (config 001): de-normalise, clamp to [0, 1]
+            a = (out_timed[:gold.shape[0]].cpu().double() + mean).clamp(0, 1)
+            b = (gold.double() + mean).clamp(0, 1)
+            mse = float(((a - b) ** 2).mean())
+            parity["psnr_vs_reference_golden_db"] = float("inf") if mse == 0 else float(10 * __import__("math").log10(1.0 / mse))
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()
             val, ms, kind, cpu_out = cpu_reference_sample(3, 1, threads, crops=1)

@@ -355,6 +355,15 @@ static bool tc_nsplit() {
   const char* e = getenv("CIAOSR_HEAD_NSPLIT");
   return e && atoi(e) == 1;
 }
+// CIAOSR_TC_TERMS (read at every call): product terms of the pair / query MLP jobs.  7 (default) = fp16 hi/lo split with three
+// UMMAs per product (fp32-grade, the only mode inside the parity tolerance); 3 = A.W_hi (weights at 11 bits); 2 = A_hi.W_hi
+// (single fp16 pass).  The reduced modes exist to document the cost / accuracy frontier on hardware; they
+// apply to the pair / query MLP kernels only (the LR precompute, cross-scale attention and encoder keep all terms).
+static unsigned tc_terms() {
+  const char* e = getenv("CIAOSR_TC_TERMS");
+  const int v = e ? atoi(e) : 7;
+  return (v == 2 || v == 3) ? (unsigned)v : 7u;
+}
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
 // the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the
 // kernel's header); ignored when its constants do not fit beside the operand slabs (very wide heads).
@@ -435,11 +444,13 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
   P.blob = blob + t.pair_blob; P.units_per_tile = t.pair_units; P.units5 = t.units5;
   P.x_hi = b.x_hi; P.x_lo = b.x_lo; P.total_rows = total_q * 4; P.n_tiles = (int)((P.total_rows + ROWS - 1) / ROWS);
   P.softmax_scale = L.softmax_scale;
+  P.terms = tc_terms();
   QueryParams Qp;
   Qp.Dvp = t.Dvp;
   Qp.consts = reinterpret_cast<const float*>(blob + t.query_consts);
   Qp.blob = blob + t.query_blob; Qp.units_per_tile = t.query_units; Qp.slabs1 = t.slabs1;
   Qp.lr = a.lr; Qp.coord = a.coord; Qp.H = a.H; Qp.W = a.W; Qp.Q = a.Q;
+  Qp.terms = tc_terms();
   Qp.out = a.out; Qp.total_q = total_q; Qp.n_tiles = (int)((total_q + ROWS - 1) / ROWS);
   CUtensorMap map_hi, map_lo;
   if ((rc = tma_make_map_2d(&map_hi, b.x_hi, b.x_rows, t.Dvp)) || (rc = tma_make_map_2d(&map_lo, b.x_lo, b.x_rows, t.Dvp)))

@@ -46,6 +46,16 @@ constexpr int CW_A_READY = 0, CW_A_FREE = 4, CW_W_FULL = 8, CW_W_EMPTY = 16, CW_
 constexpr int CW_FIXED_BYTES = 32 * CW_T_LD * 4 + 64 * 4 + CW_NBARS * 8 + 16;
 
 struct ConvDst { split_t* hi; split_t* lo; int ld; int choff; };
+#ifdef CIAOSR_CONV_STATS
+// diagnostic build (tools/conv_issuer_stats.py): the issuer's clock64 deltas around its three mbarrier waits, accumulated in
+// registers and added up once per CTA -- [0] wait W_FULL, [1] wait A_READY, [2] wait D_FREE, [3] total, [4] taps, [5] tiles, [6] CTAs
+__device__ unsigned long long g_conv_stats[8];
+#define CONV_STAT_BEGIN() const long long stat_c0 = clock64()
+#define CONV_STAT_END(acc) acc += clock64() - stat_c0
+#else
+#define CONV_STAT_BEGIN() do {} while (0)
+#define CONV_STAT_END(acc) do {} while (0)
+#endif
 
 struct ConvParams {
   int B, H, W, tiles_x, tiles_y, n_tiles;
@@ -140,18 +150,28 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
     const uint32_t idesc = make_idesc_split(ROWS, 128);
     const uint32_t bhw = (uint32_t)((P.box_x * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
     uint32_t acnt = 0, wcnt = 0, job = 0;
+#ifdef CIAOSR_CONV_STATS
+    long long tw = 0, ta = 0, td = 0;
+    const long long tstart = clock64();
+#endif
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++job) {
       const uint32_t d = job & 1, n = job >> 1;
+      { CONV_STAT_BEGIN();
       mbar_wait(bars + 8 * (CW_D_FREE + d), (n + 1) & 1, 420);
+      CONV_STAT_END(td); }
       tc_fence_after();
       const uint32_t dcol = tmem_base + d * 128;
       for (int cb = 0; cb < P.cblocks; ++cb, ++acnt) {
         const int ast = acnt % CW_A_STAGES;
+        { CONV_STAT_BEGIN();
         mbar_wait(bars + 8 * (CW_A_READY + ast), (acnt / CW_A_STAGES) & 1, 430 + ast);
+        CONV_STAT_END(ta); }
         const uint32_t x_hi = sbase + (uint32_t)(2 * ast) * P.half_bytes, x_lo = x_hi + P.half_bytes;
         for (int tap = 0; tap < P.ntaps; ++tap, ++wcnt) {
           const int wst = wcnt % CW_W_STAGES;
+          { CONV_STAT_BEGIN();
           mbar_wait(bars + 8 * (CW_W_FULL + wst), (wcnt / CW_W_STAGES) & 1, 440 + wst);
+          CONV_STAT_END(tw); }
           tc_fence_after();
           if (lane == 0) {
             const uint32_t toff = (uint32_t)((tap / 3) * P.box_x + tap % 3) * 128u;
@@ -171,6 +191,14 @@ convw_tc_kernel(const ConvParams P, const __grid_constant__ CUtensorMap map_hi,
       if (lane == 0) umma_commit(bars + 8 * (CW_D_READY + d));
       __syncwarp();
     }
+#ifdef CIAOSR_CONV_STATS
+    if (lane == 0) {
+      atomicAdd(&g_conv_stats[0], (unsigned long long)tw); atomicAdd(&g_conv_stats[1], (unsigned long long)ta);
+      atomicAdd(&g_conv_stats[2], (unsigned long long)td); atomicAdd(&g_conv_stats[3], (unsigned long long)(clock64() - tstart));
+      atomicAdd(&g_conv_stats[4], (unsigned long long)wcnt); atomicAdd(&g_conv_stats[5], (unsigned long long)job);
+      atomicAdd(&g_conv_stats[6], 1ull);
+    }
+#endif
   } else if (warp >= 8) {
     // ---- weight stagers: row r of every K-slab, global -> registers -> tensor memory ----
     // warps 8-11 stage K columns 0-31 of every slab (TMEM columns 0-15 of its stage), warps 12-15 the rest;
@@ -605,6 +633,15 @@ extern "C" int ciaosr_debug_wait_read_rdn(unsigned long long* cycles, unsigned l
     cudaMemcpyToSymbol(ciaosr::tc::g_wait_cycles, z, 64 * 8);
     cudaMemcpyToSymbol(ciaosr::tc::g_wait_count, z, 64 * 8);
   }
+  return 0;
+}
+#endif
+
+#ifdef CIAOSR_CONV_STATS
+extern "C" int ciaosr_debug_conv_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ciaosr::g_conv_stats, 8 * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ciaosr::g_conv_stats, z, 8 * 8); }
   return 0;
 }
 #endif

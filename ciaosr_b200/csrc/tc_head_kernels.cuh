@@ -30,6 +30,7 @@ struct PairParams {
   split_t* x_hi; split_t* x_lo;   // [total_q, Dvp] attended values, already split for the query kernel's UMMAs
   long long total_rows; int n_tiles; int iters;     // iters = tiles per CTA (uniform over the grid)
   float softmax_scale;
+  uint32_t terms;             // product terms of the UMMA jobs (TcShared::terms); 7 unless CIAOSR_TC_TERMS says otherwise
 };
 // consts layout (x256 floats): 0..3 rc_k, 4 b1_k, 5..7 b_k(layers 2..4), 8..11 rc_v, 12 b1_v, 13..15 b_v(2..4),
 //                               then bv5p[Dvp] (last value Linear bias, tap-major, zero padded)
@@ -305,7 +306,8 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
 template <int CL>
 __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
+  TcShared s = tc_carve(smem);
+  s.terms = P.terms;
   for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
 #ifdef CIAOSR_TC_TIMING
   if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
@@ -371,6 +373,7 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
   extern __shared__ __align__(1024) uint8_t smem[];
   TcShared s = tc_carve(smem);
   s.pair_rank = (int)cluster_ctarank();
+  s.terms = P.terms;
   for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += 128 + 128 * PARTS) s.consts[i] = P.consts[i];
 #ifdef CIAOSR_TC_TIMING
   if (blockIdx.x == 0 && threadIdx.x == 0) tc::g_trace_on = tc::g_trace_req;
@@ -442,6 +445,7 @@ struct QueryParams {
   const uint8_t* blob; int units_per_tile; int slabs1;
   const float* lr; const float* coord; int H, W, Q;
   float* out; long long total_q; int n_tiles; int iters;
+  uint32_t terms;
 };
 
 // Row-thread work of ONE query tile (128 queries): drain layer 1 (its operand slabs are TMA-loaded by the producer warp),
@@ -511,7 +515,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1)
 query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi,
                  const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const TcShared s = tc_carve(smem);
+  TcShared s = tc_carve(smem);
+  s.terms = P.terms;
   for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
   const uint32_t tmem_base = tc_prologue<CL, NEPI>(s, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -593,6 +598,7 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
     s.bar = base + FU_BAR;
     s.consts = reinterpret_cast<float*>(smem + FU_CONST);
     s.xchg = reinterpret_cast<float*>(smem + FU_XCHG);
+    s.terms = P.terms;
   }
   const int qoff = fused_query_const_off(P.Dvp);
   for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];

@@ -62,6 +62,9 @@ struct TcShared {
   float* consts;
   float* xchg;
   int pair_rank = -1;      // >= 0: CTA-pair mode (cta_group::2 UMMAs issued by rank 0): this CTA's rank in the pair
+  // product terms the issuer accumulates: 1 = A_lo.W_hi, 2 = A_hi.W_hi, 4 = A_hi.W_lo.  7 = the fp32-grade default; 2 / 3 are
+  // the opt-in reduced-precision modes (CIAOSR_TC_TERMS, DESIGN.md 4 "cost / accuracy frontier"), outside the parity tolerance
+  uint32_t terms = 7;
 };
 
 __device__ __forceinline__ TcShared tc_carve(uint8_t* smem) {
@@ -215,6 +218,56 @@ __device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo32, uint32
       : "memory");
 }
 
+// The twelve UMMAs of one K-slab as TWO asm statements (8 on the W_hi stage pair, 4 on W_lo).  Every separate `asm volatile`
+// with register operands costs the issuing thread ~10 SASS instructions (R2UR moves into uniform registers around each
+// UTCHMMA) on a sub-partition it shares with busy row warps; with the descriptor arithmetic inside the block that is paid
+// once per group (r03h: the issuer's instruction stream, not the tensor pipe, paced the convolution kernel).
+#define CIAOSR_UMMA_SLAB_FNS(NAME, CG)                                                                                        \
+  __device__ __forceinline__ void NAME##_hi(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,         \
+                                            uint32_t acc_first) {                                                            \
+    asm volatile(                                                                                                            \
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 x, y, z;\n\t"                                                 \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                          \
+        "mov.b64 db, {%3, %5};\n\tmov.b64 da, {%1, %5};\n\t"                                                                 \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, p;\n\t"                                                    \
+        "mov.b64 da, {%2, %5};\n\t"                                                                                          \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "add.u32 x, %1, 2;\n\tadd.u32 y, %2, 2;\n\tadd.u32 z, %3, 2;\n\t"                                                    \
+        "mov.b64 db, {z, %5};\n\tmov.b64 da, {x, %5};\n\t"                                                                   \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "mov.b64 da, {y, %5};\n\t"                                                                                           \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "add.u32 x, %1, 4;\n\tadd.u32 y, %2, 4;\n\tadd.u32 z, %3, 4;\n\t"                                                    \
+        "mov.b64 db, {z, %5};\n\tmov.b64 da, {x, %5};\n\t"                                                                   \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "mov.b64 da, {y, %5};\n\t"                                                                                           \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "add.u32 x, %1, 6;\n\tadd.u32 y, %2, 6;\n\tadd.u32 z, %3, 6;\n\t"                                                    \
+        "mov.b64 db, {z, %5};\n\tmov.b64 da, {x, %5};\n\t"                                                                   \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t"                                                    \
+        "mov.b64 da, {y, %5};\n\t"                                                                                           \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, 1;\n\t}" ::"r"(d),                                         \
+        "r"(a_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(DESC_HI), "r"(acc_first)                                            \
+        : "memory");                                                                                                         \
+  }                                                                                                                          \
+  __device__ __forceinline__ void NAME##_lo(uint32_t d, uint32_t a_hi, uint32_t b_lo, uint32_t idesc) {                      \
+    asm volatile(                                                                                                            \
+        "{\n\t.reg .b64 da, db;\n\t.reg .b32 x, z;\n\t"                                                                     \
+        "mov.b64 db, {%2, %4};\n\tmov.b64 da, {%1, %4};\n\t"                                                                 \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %3, 1;\n\t"                                                    \
+        "add.u32 x, %1, 2;\n\tadd.u32 z, %2, 2;\n\tmov.b64 db, {z, %4};\n\tmov.b64 da, {x, %4};\n\t"                         \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %3, 1;\n\t"                                                    \
+        "add.u32 x, %1, 4;\n\tadd.u32 z, %2, 4;\n\tmov.b64 db, {z, %4};\n\tmov.b64 da, {x, %4};\n\t"                         \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %3, 1;\n\t"                                                    \
+        "add.u32 x, %1, 6;\n\tadd.u32 z, %2, 6;\n\tmov.b64 db, {z, %4};\n\tmov.b64 da, {x, %4};\n\t"                         \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %3, 1;\n\t}" ::"r"(d),                                         \
+        "r"(a_hi), "r"(b_lo), "r"(idesc), "r"(DESC_HI)                                                                       \
+        : "memory");                                                                                                         \
+  }
+CIAOSR_UMMA_SLAB_FNS(umma_slab1, "1")
+CIAOSR_UMMA_SLAB_FNS(umma_slab2, "2")
+#undef CIAOSR_UMMA_SLAB_FNS
+
 template <int CL>
 __device__ __forceinline__ void release_stage(const TcShared& s, int stage) {
   if (CL == 1) umma_commit(bar_at(s, w_empty_bar(stage)));
@@ -252,10 +305,14 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
     m.wbits ^= 3u << hi0;
     tc_fence_after();
     if (leader) {
+      if (s.terms == 7) {
+        umma_slab1_hi(dcol, a_lo, a_hi, b_hi, idesc, sl != 0 ? 1u : 0u);
+      } else {                                         // reduced-precision modes: A_hi.W_hi (+ A_lo.W_hi)
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        umma_lo(dcol, a_lo + 2 * ks, b_hi + 2 * ks, idesc, (sl | ks) != 0 ? 1u : 0u);
-        umma_lo(dcol, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_lo(dcol, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (sl | ks) != 0 ? 1u : 0u);
+          if (s.terms & 1) umma_lo(dcol, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+        }
       }
       release_stage<CL>(s, hi0);
       release_stage<CL>(s, hi0 + 1);
@@ -267,8 +324,7 @@ __device__ __forceinline__ void mma_job(const TcShared& s, uint32_t tmem_base, M
     m.wbits ^= 3u << 2;
     tc_fence_after();
     if (leader) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_lo(dcol, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+      if (s.terms & 4) umma_slab1_lo(dcol, a_hi, b_lo, idesc);
       release_stage<CL>(s, 2);
       release_stage<CL>(s, 3);
       if (a_release) umma_commit(bar_at(s, BAR_A_FREE + slot));
@@ -393,10 +449,14 @@ __device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_ba
     m.wbits ^= 1u << sp;
     tc_fence_after();
     if (leader) {
+      if (s.terms == 7) {
+        umma_slab2_hi(dcol, a_lo, a_hi, b_hi, idesc, sl != 0 ? 1u : 0u);
+      } else {                                         // reduced-precision modes: A_hi.W_hi (+ A_lo.W_hi)
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        umma_cg2(dcol, a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, (sl | ks) != 0 ? 1u : 0u);
-        umma_cg2(dcol, a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_cg2(dcol, a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, (sl | ks) != 0 ? 1u : 0u);
+          if (s.terms & 1) umma_cg2(dcol, a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, 1u);
+        }
       }
       umma_commit_cg2(bar_at(s, w_empty_bar(sp)), 3);
     }
@@ -405,8 +465,7 @@ __device__ __forceinline__ void mma_job_pair(const TcShared& s, uint32_t tmem_ba
     m.wbits ^= 1u << (sp + 1);
     tc_fence_after();
     if (leader) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_cg2(dcol, a_hi + 2 * ks, b_lo + 2 * ks, DESC_HI, idesc, 1u);
+      if (s.terms & 4) umma_slab2_lo(dcol, a_hi, b_lo, idesc);
       umma_commit_cg2(bar_at(s, w_empty_bar(sp + 1)), 3);
       if (a_release) umma_commit_cg2(bar_at(s, BAR_A_FREE + slot), 3);
     }
@@ -487,13 +546,8 @@ __device__ __forceinline__ void mma_job_pair_split(const TcShared& s, uint32_t t
         mbar_wait(bar_at(s, w_full_bar(stage)), (m.wbits >> stage) & 1, 220);
         m.wbits ^= 1u << stage;
         if (leader) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_cg2(dcol, a_lo + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, (sl | ks) != 0 ? 1u : 0u);
-            umma_cg2(dcol, a_hi + 2 * ks, b_hi + 2 * ks, DESC_HI, idesc, 1u);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_cg2(dcol, a_hi + 2 * ks, b_lo + 2 * ks, DESC_HI, idesc, 1u);
+          umma_slab2_hi(dcol, a_lo, a_hi, b_hi, idesc, sl != 0 ? 1u : 0u);
+          umma_slab2_lo(dcol, a_hi, b_lo, idesc);
           umma_commit_cg2(bar_at(s, w_empty_bar(stage)), 3);
           if (g == 1 && sl == 3) umma_commit_cg2(bar_at(s, BAR_D_READY + 2 * d + h), 3);
         }
