@@ -343,8 +343,9 @@ static bool tc_use_pair_umma() {
   return !(e && atoi(e) == 0);
 }
 // Experiment switches of the CTA-pair kernel, both measured slower than the default on the bench workload:
-// CIAOSR_HEAD_ROWPARTS=4: four row threads per row (16 row warps) instead of two -- the row threads are bound by the
-// half-rate ALU / conversion pipes, not by latency, so twice the warps convert a slab in the same time (6.91 vs 6.83 ms);
+// CIAOSR_HEAD_ROWPARTS=4: four row threads per row (16 row warps) instead of two -- a slab's conversion is a chain of
+// latencies every warp walks in lock-step (barrier, tcgen05.ld, convert, st.shared, proxy fence, arrive), so twice the
+// warps with half the columns each convert a slab in the same 1.5 k cycles (6.91 vs 6.83 ms);
 // CIAOSR_HEAD_NSPLIT=1: two N = 128 column halves per layer with the first half's epilogue under the second half's
 // UMMAs -- fewer bubbles, but N = 128 UMMAs cost 106 cycles in the kernel against 2 x 74 ideal (6.91 vs 6.75 ms).
 static int tc_row_parts() {
@@ -367,9 +368,16 @@ static unsigned tc_terms() {
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
 // the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the
 // kernel's header); ignored when its constants do not fit beside the operand slabs (very wide heads).
-static bool tc_use_fused(int Dvp) {
-  const char* e = getenv("CIAOSR_HEAD_FUSED");
-  return e && atoi(e) == 1 && fused_smem_bytes(Dvp) <= 227 * 1024;
+// Without the variable the fused kernel is chosen automatically when the two-kernel path's x buffer would exceed
+// CIAOSR_X_WORKSPACE_GIB (default 16 GiB): an un-tiled x8 call producing a 4K frame needs 21 GB of x, an 8K frame 85 GB --
+// where the reference's eval_bsize loop keeps memory bounded, this engine switches to its O(1)-workspace kernel instead of
+// failing with an out-of-memory error.  CIAOSR_HEAD_FUSED=0 forces the two-kernel path.
+static bool tc_use_fused(int Dvp, long long total_q) {
+  if (fused_smem_bytes(Dvp) > 227 * 1024) return false;
+  if (const char* e = getenv("CIAOSR_HEAD_FUSED")) return atoi(e) == 1;
+  double limit_gib = 16.0;
+  if (const char* e = getenv("CIAOSR_X_WORKSPACE_GIB")) limit_gib = atof(e);
+  return (double)total_q * Dvp * 2.0 * sizeof(split_t) > limit_gib * 1073741824.0;
 }
 
 static TcBufs tc_carve_ws(Arena& a, const PlanLayout& L, int B, int H, int W, int Q) {
@@ -382,7 +390,7 @@ static TcBufs tc_carve_ws(Arena& a, const PlanLayout& L, int B, int H, int W, in
   // attended values, fp16 hi / lo halves: the whole call for the two-kernel path, one 128-row block per CTA when fused
   const long long total_q = (long long)B * Q;
   s.x_rows = total_q;
-  if (tc_use_fused(t.Dvp)) {
+  if (tc_use_fused(t.Dvp, total_q)) {
     const int n_super = (int)((total_q + ROWS - 1) / ROWS);
     s.x_rows = (long long)tc_grid(n_super, tc_cluster_size()) * ROWS;          // one block per CTA (head_fused_kernel)
   }
@@ -455,7 +463,7 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
   CUtensorMap map_hi, map_lo;
   if ((rc = tma_make_map_2d(&map_hi, b.x_hi, b.x_rows, t.Dvp)) || (rc = tma_make_map_2d(&map_lo, b.x_lo, b.x_rows, t.Dvp)))
     return rc;
-  if (tc_use_fused(t.Dvp)) {
+  if (tc_use_fused(t.Dvp, total_q)) {
     // pair tiles and the query tile of the same 128 queries in one persistent CTA; x through an L2-resident scratch block.
     // The stage timer attributes the whole kernel to the pair stage (the query MLP is ~9 % of its tensor work).
     StageScope sc(3, st);

@@ -324,7 +324,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2, one issue slot for two IEEE fp32 operations) ------------------
-// The row threads of the head kernels are issue-bound once the UMMAs are cheap (CTA-pair mode, r02p: 147 k warp
+// The row threads of the head kernels are the critical path once the UMMAs are cheap (CTA-pair mode, r02p: 147 k warp
 // instructions per tile at IPC 1.4); their element-wise work -- bias adds, the layer-1 FMAs, the v - hi subtractions of
 // the operand split -- runs on pairs.  Results are bit-identical to the scalar forms (same rounding, no contraction).
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
@@ -385,7 +385,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 }
 // split of relu(v): the ReLU rides on the conversions (cvt ... .relu clamps negative results to +0), which removes one
-// FMNMX per element from the row threads (they are bound by the half-rate ALU / conversion pipes, r02w).  hi is rounded
+// FMNMX per element from the row threads (the critical path of the pair-MLP kernel).  hi is rounded
 // TOWARD ZERO so that the residual of a positive value is never negative (a .relu on the second conversion would
 // otherwise clip it): |v - hi| < ulp_fp16(v) instead of <= ulp/2, i.e. the pair carries >= 21 instead of 22 mantissa
 // bits; negative v gives hi = 0, residual v, lo = relu(v) = 0.

@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
 // CTA-pair variant (cta_group::2, tc_pipeline.cuh "CTA-pair mode"): the two CTAs of a cluster work on 256 consecutive rows
 // with ONE M = 256 UMMA stream issued by the leader; each CTA stages half of every weight operand.  Row-thread work is
 // the same function as above (its barrier arrivals go to the leader through TcShared::pair_rank).
-// PARTS = row threads per row: 2 (384 threads) or 4 (640 threads: 16 row warps, four per SM sub-partition -- the row
-// threads are the critical path of this kernel and latency-bound at two warps per sub-partition).
+// PARTS = row threads per row: 2 (384 threads, default) or 4 (640 threads: 16 row warps, four per SM sub-partition; an
+// experiment -- measured no faster, see tc_row_parts() in head_tc_engine.cu).
 // NSPLIT: the N-split issue schedule of tc_pipeline.cuh (two N = 128 column halves per layer, epilogue of the first
 // half under the UMMAs of the second) instead of one N = 256 stream per layer.
 template <int PARTS, bool NSPLIT>

@@ -821,6 +821,11 @@ def test_fused_head_kernel_matches_two_kernel_path(monkeypatch):
     assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") == plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
     monkeypatch.delenv("CIAOSR_HEAD_FUSED", raising=False)
     assert plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05") > 3 * plan.workspace_bytes(1, 16, 16, 1_000_000, "tcgen05")
+    # ... and it takes over by itself when the two-kernel path's x buffer would pass 16 GiB (40 M queries: 102 GB of x),
+    # where the reference's eval_bsize loop keeps memory bounded
+    assert plan.workspace_bytes(1, 16, 16, 40_000_000, "tcgen05") < plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05")
+    monkeypatch.setenv("CIAOSR_HEAD_FUSED", "0")
+    assert plan.workspace_bytes(1, 16, 16, 40_000_000, "tcgen05") > 9 * plan.workspace_bytes(1, 16, 16, 4_000_000, "tcgen05")
 
 
 def test_cta_pair_umma_path_matches_default(monkeypatch):
