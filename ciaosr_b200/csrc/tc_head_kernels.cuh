@@ -42,8 +42,9 @@ struct PairParams {
 // the issuer sees slab 0 ~2 k cycles earlier than with the wait in front.  Returns k.L4's accumulator index.
 // WAITK = 2 (the NEXT tile's key layer 1, written before this tile's last value chunk is reduced): same, the wait is for
 // the last accumulator of this tile (`wait_halves` column halves).
+struct L1Result { EpiState e; uint32_t dk; };      // pipeline state by value, see epi_hidden
 template <int PARTS, int WAITK>
-__device__ __noinline__ uint32_t gen_layer1(const TcShared& s, EpiState& e, int row, int half, const PairInfo& p,
+__device__ __noinline__ L1Result gen_layer1(const TcShared s, EpiState e, int row, int half, const PairInfo p,
                                                const float* __restrict__ P, const float* __restrict__ rc_s,
                                                const float* __restrict__ b1_s, int wait_halves = 2) {
   uint32_t dk = 0;
@@ -88,7 +89,7 @@ __device__ __noinline__ uint32_t gen_layer1(const TcShared& s, EpiState& e, int 
     if (s.pair_rank < 0 || sl < 2) slab_done(s, sl);     // CTA-pair mode: slabs 2 + 3 share a fence (see epi_hidden)
     else if (sl & 1) slabs_done2(s, sl - 1, sl);
   }
-  return dk;
+  return L1Result{e, dk};
 }
 
 // Row-thread work of ONE pair tile (128 (query, neighbour) rows = 32 queries): layer 1 of both chains from the LR hoists,
@@ -121,13 +122,15 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
 
       // ---- key chain -----------------------------------------------------------------------
       if (threadIdx.x == EPI_T0) TC_TRACE(3000);       // tile start
-      if (first) gen_layer1<PARTS, 0>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID);   // else: written by the previous tile
+      if (first) e = gen_layer1<PARTS, 0>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID).e;   // else: written by the previous tile
       if (threadIdx.x == EPI_T0) TC_TRACE(3001);       // k.L1 written
-      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 5 * HID);
-      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 6 * HID);
+      e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 5 * HID);
+      e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 6 * HID);
       // k.L4 is complete once both accumulator halves are; that also frees the operand slabs, so the value
       // chain's layer 1 is built FIRST: the UMMAs of v.L2 then run while the logits are reduced from D.
-      const uint32_t dk = gen_layer1<PARTS, 1>(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      const L1Result l1v = gen_layer1<PARTS, 1>(s, e, row, half, p, P.Pv, cst + 8 * HID, cst + 12 * HID);
+      e = l1v.e;
+      const uint32_t dk = l1v.dk;
       if (threadIdx.x == EPI_T0) TC_TRACE(3003);       // v.L1 written
       float logit = 0.0f;
       {
@@ -185,9 +188,9 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
       const int pix = p.pix;
       p = pair_info_of(P, next_tile, row);
       // ---- value chain (layer 1 was built above) ----------------------------------------------------
-      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 13 * HID);
-      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 14 * HID);
-      epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
+      e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 13 * HID);
+      e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 14 * HID);
+      e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 15 * HID);   // h4v -> operand of the last Linear
 
       // geometry of this row's latent code for the value gather
       int py = 0, px = 0;
@@ -237,7 +240,11 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
         // last chunk: once its accumulator is complete every UMMA of this tile is, and the operand slots are free:
         // the next tile's k.L1 goes in first, then this chunk is reduced while the tensor pipe runs the next tile's k.L2
         const bool ahead = c == nchunks5 - 1 && next_tile >= 0;
-        if (ahead) d = gen_layer1<PARTS, 2>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID, units);
+        if (ahead) {
+          const L1Result l1n = gen_layer1<PARTS, 2>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID, units);
+          e = l1n.e;
+          d = l1n.dk;
+        }
         uint32_t buf[2][CW];
         float4 vb[NV];
         load_values(c * 256 + half * CW, vb);
@@ -457,9 +464,9 @@ __device__ __forceinline__ void query_tile_rows(const TcShared& s, EpiState& e, 
       const bool valid = tile < P.n_tiles && g < P.total_q;
       // layer-1 operand slabs are written by the producer warp (TMA); keep the slot parity bookkeeping in step
       for (int sl = 0; sl < P.slabs1; ++sl) e.afree_bits ^= 1u << (sl & 3);
-      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst);
-      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + HID);
-      epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + 2 * HID);
+      e = epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst);
+      e = epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + HID);
+      e = epi_hidden<true, 2>(s, e, lane_taddr, row, half, cst + 2 * HID);
       // last hidden layer + the 256 -> 3 Linear on CUDA cores (each thread: its 32 columns of every slab)
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       {

@@ -621,9 +621,12 @@ __device__ __forceinline__ void epi_release_d(const TcShared& s, EpiState& e) {
 // Columns 0..127 are converted as soon as the first accumulator half is complete.
 // (not inlined: it is instantiated once and called per layer -- the fully unrolled body is ~400
 // instructions, and inlining it 5x per tile made instruction fetch 17 % of the row warps' stall time)
+// (state by VALUE: the body is full of `asm volatile(... ::: "memory")`, after each of which everything that lives in
+// memory -- as by-reference arguments of a non-inlined function do -- is re-loaded from the stack: 34 LDL per call sat in
+// the middle of the per-slab latency chain; in registers the pipeline state costs nothing)
 template <bool WAIT_FREE, int HALVES>
-__device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t lane_taddr, int row, int half,
-                                           const float* __restrict__ bias_s) {
+__device__ __noinline__ EpiState epi_hidden(const TcShared s, EpiState e, uint32_t lane_taddr, int row, int half,
+                                               const float* __restrict__ bias_s) {
   constexpr int CW = HALVES == 4 ? 16 : 32;      // columns per chunk
   constexpr int NCH = HID / (CW * HALVES);       // chunks this thread handles
   constexpr int PER_HALF = NCH / 2;
@@ -663,6 +666,7 @@ __device__ __noinline__ void epi_hidden(const TcShared& s, EpiState& e, uint32_t
     if (threadIdx.x == EPI_T0) TC_TRACE(2020 + sl);    // rows: this warp's part of slab sl written (published if odd / single mode)
   }
   epi_release_d(s, e);
+  return e;
 }
 
 }  // namespace ciaosr
