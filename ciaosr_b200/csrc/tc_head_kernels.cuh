@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) pair_mlp_kernel(const PairPar
     }
   } else if (warp == 1) {
     MmaState m{0, 0, 0};
-#define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an)
+// a_release = false: the row threads of this kernel never wait on A_FREE (every operand slot is rewritten only after the
+// accumulator that read it was observed complete), so it is not committed either (synccheck: arrivals nobody waits for)
+#define PAIR_MMA(ns, un, an) mma_job<CL>(s, tmem_base, m, ns, un, an, false)
     for (int it = 0; it < P.iters; ++it) {
       for (int j = 0; j < 6; ++j) PAIR_MMA(4, 2, true);
       for (int c = 0; c < nchunks5; ++c) PAIR_MMA(4, min(2, P.units5 - 2 * c), c == 0);
@@ -413,11 +415,11 @@ pair_mlp_pair_kernel(const PairParams P, const __grid_constant__ CUtensorMap wma
       for (int it = 0; it < P.iters; ++it) {
         for (int j = 0; j < 6; ++j) {
           if (NSPLIT) mma_job_pair_split(s, tmem_base, m, 2, true);
-          else mma_job_pair(s, tmem_base, m, 4, 2, true);
+          else mma_job_pair(s, tmem_base, m, 4, 2, true, false);          // a_release = false: see PAIR_MMA above
         }
         for (int c = 0; c < nchunks5; ++c) {
           if (NSPLIT) mma_job_pair_split(s, tmem_base, m, min(2, P.units5 - 2 * c), c == 0);
-          else mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+          else mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0, false);
         }
       }
     }
@@ -633,8 +635,7 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
         }
       }
       // x of this super-tile is complete (and visible to the async proxy) once every row warp has arrived.  All of the
-      // pair phase's A_FREE completions (an even number per slot) have happened by then, so the slot parities below
-      // continue exactly as in query_mlp_kernel.
+      // pair phase never commits A_FREE, so the slot parities below continue exactly as in query_mlp_kernel.
       mbar_wait(bar_at(s, BAR_X_READY), it & 1, 130);
       const uint8_t* b = Q.blob;
       produce_job_tma_a<CL, NEPI>(s, ps, afree_bits, b, Q.slabs1, 2, cta_rank, &map_hi, &map_lo, 0, scratch_row0);
@@ -646,8 +647,9 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
     MmaState m{0, 0, 0};
     for (int it = 0; it < Q.iters; ++it) {
       for (int sub = 0; sub < 4; ++sub) {
-        for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
-        for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0);
+        // pair phase: A_FREE is neither waited on nor committed (see PAIR_MMA); the query phase below uses it
+        for (int j = 0; j < 6; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true, false);
+        for (int c = 0; c < nchunks5; ++c) mma_job<CL>(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0, false);
       }
       mma_job<CL>(s, tmem_base, m, Q.slabs1, 2, true);
       for (int j = 0; j < 3; ++j) mma_job<CL>(s, tmem_base, m, 4, 2, true);
