@@ -348,6 +348,11 @@ static bool tc_use_pair_umma() {
 // warps with half the columns each convert a slab in the same 1.5 k cycles (6.91 vs 6.83 ms);
 // CIAOSR_HEAD_NSPLIT=1: two N = 128 column halves per layer with the first half's epilogue under the second half's
 // UMMAs -- fewer bubbles, but N = 128 UMMAs cost 106 cycles in the kernel against 2 x 74 ideal (6.91 vs 6.75 ms).
+// CIAOSR_QUERY_PAIR=0: the query MLP on the single-CTA kernel even when the pair-MLP stage runs as CTA pairs
+static bool tc_query_single() {
+  const char* e = getenv("CIAOSR_QUERY_PAIR");
+  return e && atoi(e) == 0;
+}
 static int tc_row_parts() {
   const char* e = getenv("CIAOSR_HEAD_ROWPARTS");
   return (e && atoi(e) == 4) ? 4 : 2;
@@ -508,7 +513,16 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
                       : launch_clustered(pair_mlp_kernel<1>, grid, 1, SM_TOTAL, st, P);
     if (rc2) return rc2;
   }
-  {
+  if (tc_use_pair_umma() && !tc_query_single()) {
+    StageScope sc(4, st);
+    static DynSmemOptIn optin_qpair;
+    if ((rc = optin_qpair.ensure(query_mlp_pair_kernel, SM_TOTAL))) return rc;
+    CUtensorMap qwmap;
+    if ((rc = tma_make_map_linear_rows(&qwmap, blob + t.query_blob, (long long)t.query_units * 2 * ROWS))) return rc;
+    const int grid = tc_grid(Qp.n_tiles, 2);
+    Qp.iters = (Qp.n_tiles + grid - 1) / grid;
+    if ((rc = launch_clustered(query_mlp_pair_kernel, grid, 2, SM_TOTAL, st, Qp, map_hi, map_lo, qwmap))) return rc;
+  } else {
     StageScope sc(4, st);
     const int grid = tc_grid(Qp.n_tiles, CL);
     Qp.iters = (Qp.n_tiles + grid - 1) / grid;

@@ -567,6 +567,56 @@ query_mlp_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi
 }
 
 
+// CTA-pair variant of the query kernel (cta_group::2): two query tiles per cluster, M = 256 UMMAs issued by the leader, each
+// CTA stages half of every weight operand (the single-CTA kernel pays 189 cycles per N = 256 UMMA -- 12 KB of shared-memory
+// operand reads each -- the pair ~150).  Row-thread work is query_tile_rows unchanged.
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+query_mlp_pair_kernel(const QueryParams P, const __grid_constant__ CUtensorMap map_hi,
+                      const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap wmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  TcShared s = tc_carve(smem);
+  s.pair_rank = (int)cluster_ctarank();
+  s.terms = P.terms;
+  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  const uint32_t tmem_base = tc_prologue_pair<NEPI>(s, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+
+  if (warp == 0) {
+    ProdState ps{0};
+    uint32_t afree_bits = 0xFu;
+    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); tma_prefetch_desc(&wmap); }
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;
+      const int row0 = (int)min(tile * ROWS, (long long)0x7FFFFF00);     // past the end: all rows read as zero
+      long long r = 0;                                                   // 128-byte row of the weight blob
+      produce_job_tma_a_pair<NEPI>(s, ps, afree_bits, &wmap, r, P.slabs1, 2, &map_hi, &map_lo, row0);
+      r += (long long)P.slabs1 * 2 * 2 * ROWS;
+      for (int j = 0; j < 3; ++j) { produce_job_pair(s, ps, &wmap, r, 4, 2); r += 4 * 2 * 2 * ROWS; }
+      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;        // layers 2..4: each slot written once by the row threads
+    }
+  } else if (warp == 1) {
+    if (s.pair_rank == 0) {
+      MmaState m{0, 0, 0};
+      for (int it = 0; it < P.iters; ++it) {
+        mma_job_pair(s, tmem_base, m, P.slabs1, 2, true);
+        for (int j = 0; j < 3; ++j) mma_job_pair(s, tmem_base, m, 4, 2, true);
+      }
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu, 0};
+    const float* cst = s.consts;
+    for (int it = 0; it < P.iters; ++it) {
+      const long long tile = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;
+      query_tile_rows(s, e, P, cst, lane_taddr, row, half, tile);
+    }
+  }
+  tc_teardown_pair(tmem_base);
+}
+
 // =====================================================================================================
 // fused head kernel: per 128 queries, 4 pair tiles + 1 query tile in ONE persistent CTA  (opt-in)
 // =====================================================================================================

@@ -409,6 +409,39 @@ __device__ __forceinline__ void produce_job_pair(const TcShared& s, ProdState& p
   }
 }
 
+// CTA-pair form of produce_job_tma_a: each CTA lands ITS 128 operand rows of every K-slab in its own slots (2-D tensor
+// loads in the .cta_group::2 form, so the bytes of both CTAs count on the LEADER's A_READY, which carries
+// 2 x NEPI/32 arrivals: the leader's producer supplies all of them, one with the transaction bytes of both CTAs) and
+// interleaves them with its half of the slab's weights.  A_FREE is local to each CTA (multicast commit of the leader).
+template <int NEPI>
+__device__ __forceinline__ void produce_job_tma_a_pair(const TcShared& s, ProdState& ps, uint32_t& afree_bits,
+                                                       const CUtensorMap* wmap, long long wrow0, int nslabs, int units,
+                                                       const CUtensorMap* map_hi, const CUtensorMap* map_lo, int row0) {
+  const int lane = threadIdx.x & 31;
+  int a_next = 0;
+  for (int sl = 0; sl < nslabs; ++sl) {
+    while (a_next < nslabs && a_next <= sl + 3) {
+      const int slot = a_next & 3;
+      const uint32_t fr = bar_at(s, BAR_A_FREE + slot), par = (afree_bits >> slot) & 1;
+      if (a_next == sl) mbar_wait(fr, par, 120 + slot);
+      else if (!__shfl_sync(0xffffffffu, (int)mbar_try_wait(fr, par), 0)) break;
+      afree_bits ^= 1u << slot;
+      if (lane == 0) {
+        const uint32_t rdy = bar_at(s, BAR_A_READY + slot);
+        if (s.pair_rank == 0) {
+          mbar_arrive_expect_tx(rdy, 4 * SLAB_BYTES);                 // hi + lo slabs of both CTAs
+          for (int k = 1; k < 2 * NEPI / 32; ++k) mbar_arrive(rdy);
+        }
+        tma_load_2d_cg2(s.a_hi + slot * SLAB_BYTES, map_hi, a_next * KSLAB, row0, rdy);
+        tma_load_2d_cg2(s.a_lo + slot * SLAB_BYTES, map_lo, a_next * KSLAB, row0, rdy);
+      }
+      __syncwarp();
+      ++a_next;
+    }
+    produce_job_pair(s, ps, wmap, wrow0 + (long long)sl * units * 2 * ROWS, 1, units);
+  }
+}
+
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
 #if defined(CIAOSR_TC_TIMING) && !defined(CIAOSR_TC_TRACE_ONLY)
   const long long tt = clock64();

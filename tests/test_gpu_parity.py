@@ -865,3 +865,9 @@ def test_cta_pair_umma_path_matches_default(monkeypatch):
         print(f"  N-split schedule: max-abs vs default {max_abs(outn, out):.2e}; four row threads per row: {max_abs(out4, out):.2e}")
         assert torch.equal(outn, out) and torch.equal(out4n, out4)
         assert max_abs(out4, out) < 5e-6
+        # the query MLP as CTA pairs (default) vs its single-CTA kernel: same products in the same order
+        monkeypatch.setenv("CIAOSR_QUERY_PAIR", "0")
+        outq = plan.query_rgb(feat, coord, cell, lr_image=lq, nonlocal_feat=nl, eval_bsize=30000)
+        monkeypatch.delenv("CIAOSR_QUERY_PAIR", raising=False)
+        torch.cuda.synchronize()
+        assert torch.equal(outq, out), max_abs(outq, out)
