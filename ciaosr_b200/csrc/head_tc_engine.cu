@@ -371,8 +371,8 @@ static unsigned tc_terms() {
   return (v == 2 || v == 3) ? (unsigned)v : 7u;
 }
 // CIAOSR_HEAD_FUSED=1 (read at every call) selects head_fused_kernel: x stays in a per-CTA, L2-resident scratch block and
-// the workspace no longer grows with the number of queries, at ~7 % more time than the two pipelined kernels (see the
-// kernel's header); ignored when its constants do not fit beside the operand slabs (very wide heads).
+// the workspace no longer grows with the number of queries, at ~5 % more time than the two pipelined kernels (CTA-pair
+// form head_fused_pair_kernel: 7.5 vs 7.1 ms on the bench workload; see the kernels' headers); ignored when its constants do not fit beside the operand slabs (very wide heads).
 // Without the variable the fused kernel is chosen automatically when the two-kernel path's x buffer would exceed
 // CIAOSR_X_WORKSPACE_GIB (default 16 GiB): an un-tiled x8 call producing a 4K frame needs 21 GB of x, an 8K frame 85 GB --
 // where the reference's eval_bsize loop keeps memory bounded, this engine switches to its O(1)-workspace kernel instead of
@@ -397,7 +397,7 @@ static TcBufs tc_carve_ws(Arena& a, const PlanLayout& L, int B, int H, int W, in
   s.x_rows = total_q;
   if (tc_use_fused(t.Dvp, total_q)) {
     const int n_super = (int)((total_q + ROWS - 1) / ROWS);
-    s.x_rows = (long long)tc_grid(n_super, tc_cluster_size()) * ROWS;          // one block per CTA (head_fused_kernel)
+    s.x_rows = (long long)tc_grid(n_super, tc_use_pair_umma() ? 2 : tc_cluster_size()) * ROWS;   // one block per CTA (head_fused_*kernel)
   }
   s.x_hi = a.take<split_t>((size_t)s.x_rows * t.Dvp);
   s.x_lo = a.take<split_t>((size_t)s.x_rows * t.Dvp);
@@ -476,6 +476,18 @@ int run_head_tc(const PlanLayout& L, const float* plan, const HeadArgs& a, void*
     const int smem_bytes = fused_smem_bytes(t.Dvp);
     if ((rc = optin[0].ensure(head_fused_kernel<1>, smem_bytes)) || (rc = optin[1].ensure(head_fused_kernel<2>, smem_bytes)))
       return rc;
+    if (tc_use_pair_umma()) {                 // CTA pairs: cta_group::2 UMMAs in both phases
+      static DynSmemOptIn optin_fp;
+      if ((rc = optin_fp.ensure(head_fused_pair_kernel, smem_bytes))) return rc;
+      CUtensorMap wmap_p, wmap_q;
+      if ((rc = tma_make_map_linear_rows(&wmap_p, blob + t.pair_blob, (long long)t.pair_units * 2 * ROWS)) ||
+          (rc = tma_make_map_linear_rows(&wmap_q, blob + t.query_blob, (long long)t.query_units * 2 * ROWS)))
+        return rc;
+      const int grid = tc_grid(Qp.n_tiles, 2);
+      Qp.iters = (Qp.n_tiles + grid - 1) / grid;
+      P.iters = Qp.iters * 4;
+      return launch_clustered(head_fused_pair_kernel, grid, 2, smem_bytes, st, P, Qp, map_hi, map_lo, wmap_p, wmap_q);
+    }
     const int grid = tc_grid(Qp.n_tiles, CL);
     Qp.iters = (Qp.n_tiles + grid - 1) / grid;
     P.iters = Qp.iters * 4;

@@ -732,4 +732,92 @@ head_fused_kernel(const PairParams P, const QueryParams Q, const __grid_constant
   tc_teardown<CL>(tmem_base);
 }
 
+// CTA-pair form of the fused kernel [r2b]: the same alternation of four pair tiles and one query tile per 128 queries, with
+// the M = 256 cta_group::2 UMMAs of pair_mlp_pair_kernel / query_mlp_pair_kernel: both CTAs of a cluster walk the job
+// sequence in lock-step on their own queries and their own x scratch block (X_READY stays local to each CTA; the layer-1
+// operand loads of both CTAs count on the leader's A_READY).  Default form of the fused path when CTA pairs are on.
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+head_fused_pair_kernel(const PairParams P, const QueryParams Q, const __grid_constant__ CUtensorMap map_hi,
+                       const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap wmap_p,
+                       const __grid_constant__ CUtensorMap wmap_q) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  TcShared s;
+  {
+    const uint32_t base = smem_u32(smem);
+    s.a_hi = base + SM_A_HI; s.a_lo = base + SM_A_LO; s.w = base + SM_W;
+    s.bar = base + FU_BAR;
+    s.consts = reinterpret_cast<float*>(smem + FU_CONST);
+    s.xchg = reinterpret_cast<float*>(smem + FU_XCHG);
+    s.terms = P.terms;
+    s.pair_rank = (int)cluster_ctarank();
+  }
+  const int qoff = fused_query_const_off(P.Dvp);
+  for (int i = threadIdx.x; i < 16 * HID + P.Dvp; i += HEAD_THREADS) s.consts[i] = P.consts[i];
+  for (int i = threadIdx.x; i < 8 * HID; i += HEAD_THREADS) s.consts[qoff + i] = Q.consts[i];
+  if (threadIdx.x == 0) mbar_init(bar_at(s, BAR_X_READY), NEPI / 32);       // fenced + synced by the prologue below
+  const uint32_t tmem_base = tc_prologue_pair<NEPI>(s, smem, FU_SLOT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks5 = (P.units5 + 1) / 2;
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+  const int scratch_row0 = blockIdx.x * ROWS;            // this CTA's block of x rows
+
+  if (warp == 0) {
+    ProdState ps{0};
+    uint32_t afree_bits = 0xFu;
+    if (lane == 0) { tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); tma_prefetch_desc(&wmap_p); tma_prefetch_desc(&wmap_q); }
+    for (int it = 0; it < Q.iters; ++it) {
+      for (int sub = 0; sub < 4; ++sub) {
+        long long r = 0;
+        for (int j = 0; j < 6; ++j) { produce_job_pair(s, ps, &wmap_p, r, 4, 2); r += 4 * 2 * 2 * ROWS; }
+        for (int c = 0; c < nchunks5; ++c) {
+          const int units = min(2, P.units5 - 2 * c);
+          produce_job_pair(s, ps, &wmap_p, r, 4, units);
+          r += 4 * units * 2 * ROWS;
+        }
+      }
+      mbar_wait(bar_at(s, BAR_X_READY), it & 1, 130);   // this CTA's x block is complete and visible to the async proxy
+      long long r = 0;
+      produce_job_tma_a_pair<NEPI>(s, ps, afree_bits, &wmap_q, r, Q.slabs1, 2, &map_hi, &map_lo, scratch_row0);
+      r += (long long)Q.slabs1 * 2 * 2 * ROWS;
+      for (int j = 0; j < 3; ++j) { produce_job_pair(s, ps, &wmap_q, r, 4, 2); r += 4 * 2 * 2 * ROWS; }
+      afree_bits ^= 0xFu; afree_bits ^= 0xFu; afree_bits ^= 0xFu;
+    }
+  } else if (warp == 1) {
+    if (s.pair_rank == 0) {
+      MmaState m{0, 0, 0};
+      for (int it = 0; it < Q.iters; ++it) {
+        for (int sub = 0; sub < 4; ++sub) {
+          for (int j = 0; j < 6; ++j) mma_job_pair(s, tmem_base, m, 4, 2, true, false);
+          for (int c = 0; c < nchunks5; ++c) mma_job_pair(s, tmem_base, m, 4, min(2, P.units5 - 2 * c), c == 0, false);
+        }
+        mma_job_pair(s, tmem_base, m, Q.slabs1, 2, true);
+        for (int j = 0; j < 3; ++j) mma_job_pair(s, tmem_base, m, 4, 2, true);
+      }
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    EpiState e{0, 0xFu, 0};
+    const float* cst = s.consts;
+    const float* bv5 = s.consts + 16 * HID;
+    const float* qcst = s.consts + qoff;
+    PairInfo pinfo;
+    for (int it = 0; it < Q.iters; ++it) {
+      const long long st = ((long long)it * n_clusters + cluster_id) * 2 + s.pair_rank;      // super-tile = 128 queries
+      for (int sub = 0; sub < 4; ++sub) {
+        if (sub == 0) pinfo = pair_info_of(P, st * 4, row);
+        pair_tile_rows<2>(s, e, P, cst, bv5, lane_taddr, row, half, lane, st * 4 + sub, scratch_row0 + sub * (ROWS / 4), pinfo,
+                          sub == 0, sub < 3 ? st * 4 + sub + 1 : -1);
+      }
+      __threadfence();
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_at(s, BAR_X_READY));
+      query_tile_rows(s, e, Q, qcst, lane_taddr, row, half, st);
+    }
+  }
+  tc_teardown_pair(tmem_base);
+}
+
 }  // namespace ciaosr
