@@ -67,17 +67,23 @@ __device__ __noinline__ L1Result gen_layer1(const TcShared s, EpiState e, int ro
     const uint64_t ry = pack2(p.rel_y, p.rel_y), rx = pack2(p.rel_x, p.rel_x);
     const uint64_t sy = pack2(p.sc_y, p.sc_y), sx = pack2(p.sc_x, p.sc_x);
 #pragma unroll
-    for (int i = 0; i < CW; i += 2) {
+    for (int i = 0; i < CW; i += 4) {                  // four columns per step: one LDS.128 per constant array
       const int c = c0 + i;
-      const float2 b1 = *reinterpret_cast<const float2*>(b1_s + c);
-      const float2 r0 = *reinterpret_cast<const float2*>(rc_s + c), r1 = *reinterpret_cast<const float2*>(rc_s + HID + c);
-      const float2 r2 = *reinterpret_cast<const float2*>(rc_s + 2 * HID + c), r3 = *reinterpret_cast<const float2*>(rc_s + 3 * HID + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(b1_s + c);
+      const float4 r0 = *reinterpret_cast<const float4*>(rc_s + c), r1 = *reinterpret_cast<const float4*>(rc_s + HID + c);
+      const float4 r2 = *reinterpret_cast<const float4*>(rc_s + 2 * HID + c), r3 = *reinterpret_cast<const float4*>(rc_s + 3 * HID + c);
       uint64_t t = add2(pack2(v[i], v[i + 1]), pack2(b1.x, b1.y));
       t = fma2(pack2(r0.x, r0.y), ry, t);
       t = fma2(pack2(r1.x, r1.y), rx, t);
       t = fma2(pack2(r2.x, r2.y), sy, t);
       t = fma2(pack2(r3.x, r3.y), sx, t);
       unpack2(t, v[i], v[i + 1]);                      // the ReLU is part of the operand split (split2_relu)
+      uint64_t u = add2(pack2(v[i + 2], v[i + 3]), pack2(b1.z, b1.w));
+      u = fma2(pack2(r0.z, r0.w), ry, u);
+      u = fma2(pack2(r1.z, r1.w), rx, u);
+      u = fma2(pack2(r2.z, r2.w), sy, u);
+      u = fma2(pack2(r3.z, r3.w), sx, u);
+      unpack2(u, v[i + 2], v[i + 3]);
     }
     if (WAITK && sl == 0) {
       dk = epi_wait_half(s, e, 0);
