@@ -50,17 +50,22 @@ __device__ __noinline__ L1Result gen_layer1(const TcShared s, EpiState e, int ro
   uint32_t dk = 0;
   constexpr int CW = 64 / PARTS, NV = CW / 4;
   const float4* prow = p.pix >= 0 ? reinterpret_cast<const float4*>(P + (long long)p.pix * HID) + half * NV : nullptr;
-  float4 buf[NV];
+  // the gather of this row's four slabs runs TWO slabs ahead of the arithmetic (r03s trace: with one slab of lookahead every
+  // slab took 2.5 k cycles against 1.1 k for the same conversion work in epi_hidden -- L2 latency under the weight streams)
+  float4 buf[2][NV];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) buf[j] = prow ? __ldg(prow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) buf[q][j] = prow ? __ldg(prow + q * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
   for (int sl = 0; sl < 4; ++sl) {
     float v[CW];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) { v[4 * j] = buf[j].x; v[4 * j + 1] = buf[j].y; v[4 * j + 2] = buf[j].z; v[4 * j + 3] = buf[j].w; }
-    if (sl + 1 < 4) {
+    for (int j = 0; j < NV; ++j) { v[4 * j] = buf[sl & 1][j].x; v[4 * j + 1] = buf[sl & 1][j].y; v[4 * j + 2] = buf[sl & 1][j].z; v[4 * j + 3] = buf[sl & 1][j].w; }
+    if (sl + 2 < 4) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) buf[j] = prow ? __ldg(prow + (sl + 1) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j) buf[sl & 1][j] = prow ? __ldg(prow + (sl + 2) * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int c0 = sl * 64 + half * CW;
     // same operations in the same order as the scalar form, two columns per instruction (FADD2 / FFMA2)
