@@ -1,4 +1,4 @@
-"""world_size-2 tests of the multi-GPU host logic on CPU (gloo): sharding rules, the single
+"""world_size-2 and -3 tests of the multi-GPU host logic on CPU (gloo): sharding rules, the single
 padded all-gather, and that sharded evaluation reproduces the unsharded result."""
 import os
 
@@ -57,7 +57,7 @@ def _worker(rank, ws, port, tmp):
             got = cd.sharded_query_forward(gen, lq, coord, cell, eval_bsize=bs)
             assert got.shape == ref.shape and torch.equal(got, ref), bs
         # uneven padded gather
-        counts = [3, 1]
+        counts = [3, 1, 0, 2, 5][:ws]                    # includes a rank that contributes nothing
         t = torch.full((counts[rank], 2), float(rank))
         parts = cd.all_gather_padded(t, counts)
         assert [p.shape[0] for p in parts] == counts and float(parts[1][0, 0]) == 1.0
@@ -71,11 +71,13 @@ def _worker(rank, ws, port, tmp):
         dist.destroy_process_group()
 
 
-def test_two_rank_gloo(tmp_path):
+@pytest.mark.parametrize("ws", [2, 3])
+def test_multi_rank_gloo(tmp_path, ws):
+    """ws = 3: 5 batch items, 11 queries and 7 tiles do not divide by the world size, and one rank gathers nothing."""
     import socket
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+    mp.spawn(_worker, args=(ws, port, str(tmp_path)), nprocs=ws, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(ws))
