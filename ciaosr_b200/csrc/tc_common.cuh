@@ -69,6 +69,16 @@ __device__ __forceinline__ void tc_trace(int tag) {
     if (i < 8192) { g_trace[2 * i] = (unsigned long long)tag; g_trace[2 * i + 1] = (unsigned long long)clock64(); }
   }
 }
+// (tag, %globaltimer) event: pairs with a TC_TRACE of the same place to read the SM clock rate during the kernel
+__device__ __forceinline__ void tc_trace_ns(int tag) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_on) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 8192) { g_trace[2 * i] = (unsigned long long)tag; g_trace[2 * i + 1] = ns; }
+  }
+}
+#define TC_TRACE_NS(tag) ::ciaosr::tc::tc_trace_ns(tag)
 #define TC_TRACE(tag) ::ciaosr::tc::tc_trace(tag)
 // experiment switches of the diagnostic build (ciaosr_debug_flags): bit 0 = row threads skip their arithmetic and operand
 // stores (waits / arrivals kept), bit 1 = the weight producer of the CTA-pair kernel signals stages without loading them
@@ -76,6 +86,7 @@ static __device__ int g_dbg_flags;
 #define TC_DBG(bit) (::ciaosr::tc::g_dbg_flags & (bit))
 #else
 #define TC_DBG(bit) 0
+#define TC_TRACE_NS(tag) do {} while (0)
 #define TC_TRACE(tag) do {} while (0)
 #endif
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.

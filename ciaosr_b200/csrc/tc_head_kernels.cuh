@@ -132,7 +132,7 @@ __device__ __forceinline__ void pair_tile_rows(const TcShared& s, EpiState& e, c
       const bool valid = tile < P.n_tiles && R < P.total_rows;
 
       // ---- key chain -----------------------------------------------------------------------
-      if (threadIdx.x == EPI_T0) TC_TRACE(3000);       // tile start
+      if (threadIdx.x == EPI_T0) { TC_TRACE(3000); TC_TRACE_NS(9000); }       // tile start (+ wall clock in the trace build)
       if (first) e = gen_layer1<PARTS, 0>(s, e, row, half, p, P.Pk, cst, cst + 4 * HID).e;   // else: written by the previous tile
       if (threadIdx.x == EPI_T0) TC_TRACE(3001);       // k.L1 written
       e = epi_hidden<false, PARTS>(s, e, lane_taddr, row, half, cst + 5 * HID);

@@ -21,7 +21,13 @@ with torch.no_grad():
     model.generator(lq, coord, cell, test_mode=True)
     torch.cuda.synchronize()
 lib.ciaosr_debug_trace(0, buf, ctypes.byref(n))
-ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(min(n.value, 8192)))
+raw = [(buf[2 * i + 1], buf[2 * i]) for i in range(min(n.value, 8192))]
+ns = [t for t, tag in raw if tag == 9000]                       # %globaltimer at the tile starts
+ev = sorted((t, tag) for t, tag in raw if tag != 9000)
+cyc = [t for t, tag in ev if tag == 3000]
+if len(ns) > 2 and len(cyc) == len(ns):
+    print(f"# SM clock during the kernel: {(cyc[-1] - cyc[0]) / (ns[-1] - ns[0]) * 1e3:.0f} MHz "
+          f"({cyc[-1] - cyc[0]} cycles in {ns[-1] - ns[0]} ns over {len(ns) - 1} tiles)")
 t0 = ev[0][0]
 NAMES = {1010: "ISSUER job issued", 2010: "rows  D drained", 3000: "rows  TILE START", 3001: "rows  k.L1 written",
          3002: "rows  k.L4 complete", 3003: "rows  v.L1 written", 3004: "rows  softmax done"}
